@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- rays/s of the per-ray rendering hot path at 128 samples/ray (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2]
+
+A "step" renders one NSFF-shape frame (288x512 = 147,456 rays x 128 samples, 3 source views,
+static + dynamic encoding volumes, val mode) per GPU: gather -> tcgen05 bf16 MLP -> composite for
+the static net, then the same for the dynamic net and the blended composite.  Synthetic data,
+random-init nets (SURVEY.md 8d recipe).
+
+  value  rays/s with the ray tensors already resident in HBM (CUDA events, max over ranks)
+  e2e    the same render through the drop-in `rendering()` API fed from pinned HOST ray buffers,
+         slab by slab, host->device copies and the device->host read of the maps inside the timed
+         region
+  roofline  the dominant kernel (the tensor-core MLP, two launches per step): algorithmic FLOPs /
+         CUDA-event time measured live around those launches, against MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle port (the reference's own torch ops: grid_sample + linear) timed on
+         this box's host cores on a bounded sample of the same workload
+N > 1 (torchrun): weak scaling, every rank renders its own full frame (a different wander-path
+pose of the same time-frame) after one NCCL broadcast of the per-frame volumes / views per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (H, W, V, dynamic)
+    "cfg1": dict(H=64, W=80, V=3, dynamic=False, desc="synthetic 64x80, V=3, static volume only"),
+    "cfg2": dict(H=288, W=512, V=3, dynamic=True, desc="NSFF 288x512 full frame, V=3, static+dynamic volumes, val mode"),
+    "cfg3": dict(H=288, W=512, V=10, dynamic=True, desc="NSFF 288x512 full frame, V=10 keyframes, static+dynamic volumes"),
+}
+S = 128
+
+
+def macs_per_sample(V, dynamic):
+    """algorithmic (unpadded) MACs per sample."""
+    stat = 593408 + 256 * (8 + 4 * V) + (256 if dynamic else 0)
+    dyn = 84 * 256 + 6 * 256 * 256 + 340 * 256 + 24 * 256 + 256 + 256 * 256 + 283 * 128 + 384 + 1536 + 512
+    return stat, (dyn if dynamic else 0)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, reasons, mx = [], set(), 0
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # "under load" = upper half of the samples (idle samples before/after the timed loop are dropped)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference(cfg, n_rays, repeats, threads=None):
+    """Time the CPU oracle port on `n_rays` rays spread over the frame.  Returns rays/s (best)."""
+    import torch
+    from oracle import zest_oracle as zo
+    from zest_nerf_b200 import rays as zrays
+    from zest_nerf_b200.synthetic import make_scene
+    torch.set_num_threads(threads or os.cpu_count())
+    c = CONFIGS[cfg]
+    sc = make_scene(H=c["H"], W=c["W"], V=c["V"], pad=24, D=128, dynamic=c["dynamic"], seed=0)
+    chunk = 1024
+    n_chunks = max(1, n_rays // chunk)
+    total = c["H"] * c["W"] // chunk
+    idxs = [int(i * total / n_chunks) for i in range(n_chunks)]
+    best = None
+    with torch.no_grad():
+        for rep in range(repeats + 1):          # first repeat is the warm-up
+            t0 = time.perf_counter()
+            for i in idxs:
+                pts, rdir, ndc, z = zrays.build_rays_val(c["H"], c["W"], sc.w2cs, sc.c2ws, sc.intrinsics, sc.near_fars,
+                                                         S, pad=24, chunk=chunk, idx=i)
+                zo.rendering(sc.args, pts, ndc, z, rdir, fast=True, **sc.render_kwargs())
+            dt = time.perf_counter() - t0
+            if rep > 0:
+                best = dt if best is None else min(best, dt)
+    return n_chunks * chunk / best, torch.get_num_threads(), f"{n_chunks} x {chunk}-ray chunks spread over the frame, best of {repeats}"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    c = CONFIGS[args.config]
+    n = 2048
+    rps = []
+    cores = None
+    t_all = time.perf_counter()
+    import torch
+    for step in range(args.warmup + args.steps):
+        v, cores, sample = cpu_reference(args.config, n, 1)
+        if step >= args.warmup:
+            rps.append(v)
+        if time.perf_counter() - t_all > 240:
+            break
+    value = sum(rps) / max(1, len(rps))
+    line = {"impl": "reference", "metric": "rays_per_sec_128_samples", "value": value, "unit": "rays/s",
+            "n_gpus": args.gpus, "steps": len(rps), "warmup": args.warmup, "ms_per_step": 1e3 * n / value,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.config + ": " + c["desc"], "rays_per_step": n, "samples_per_ray": S},
+            "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
+                             "sample": f"{n} rays per step (2 x 1024-ray chunks spread over the frame); oracle port of the "
+                                       "reference (same torch CPU ops), the Python reference itself cannot travel to this box"},
+            "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=list(CONFIGS))
+    ap.add_argument("--mlp", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    if not os.path.exists(ge.LIB):
+        ge.build()
+    from zest_nerf_b200 import _lib, ops, rays as zrays
+    from zest_nerf_b200.driver import FrameRenderer
+    from zest_nerf_b200.renderer import rendering
+    from zest_nerf_b200.synthetic import make_scene
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    ops.set_mlp_mode(args.mlp)
+    c = CONFIGS[args.config]
+    H, W, V = c["H"], c["W"], c["V"]
+    R = H * W
+    sc = make_scene(H=H, W=W, V=V, pad=24, D=128, dynamic=c["dynamic"], seed=0)
+    # every rank renders its own pose (weak scaling): the wander-path idea, pose r = target shifted by r
+    c2w_tgt = sc.c2ws[0, -1].clone()
+    c2w_tgt[0, 3] += 0.01 * rank
+    sc.c2ws[0, -1] = c2w_tgt
+    sc.w2cs[0, -1] = torch.linalg.inv(c2w_tgt)
+    pts, rdir, ndc, z = zrays.build_rays_val(H, W, sc.w2cs, sc.c2ws, sc.intrinsics, sc.near_fars, S, pad=24)
+    host = [t.contiguous().pin_memory() for t in (pts, ndc, z, rdir)]
+    sc.to(dev)
+    fr = FrameRenderer(sc.net_static, sc.net_dynamic, device=dev)
+
+    def install_frame():
+        fr.set_frame(sc.vol_static, sc.imgs[:, :-1].contiguous(), sc.im_cam_mat, sc.vol_dynamic, sc.nb_imgs, sc.nb_cam_mat)
+
+    install_frame()
+    d_pts, d_ndc, d_z, d_dir = [t.to(dev) for t in host]
+    big = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # L2 flush buffer (> 126 MB L2)
+
+    def step(timers=None):
+        if world > 1:
+            install_frame()                       # per-frame NCCL broadcast + repack
+        return fr.render_rays(d_pts, d_ndc, d_z, d_dir, sc.ref_frame_idx if c["dynamic"] else None, timers)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = lib.zest_launch_count()
+    # ---------------- timed region: K steps, CUDA events, L2 flushed between steps ----------------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage_ev = []
+    barrier()
+    for k in range(args.steps):
+        big.zero_()
+        timers = []
+        ev[k][0].record()
+        out = step(timers)
+        ev[k][1].record()
+        stage_ev.append(timers)
+    barrier()
+    launches = lib.zest_launch_count() - launches0
+    ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms)
+    clocks = sampler.stop()
+    value = world * R * args.steps / (total_ms * 1e-3)
+
+    # stage breakdown + roofline of the dominant kernel (the tensor-core MLP launches)
+    stage_ms = {}
+    for timers in stage_ev:
+        for (n0, e0), (n1, e1) in zip(timers[:-1], timers[1:]):
+            stage_ms[n1] = stage_ms.get(n1, 0.0) + e0.elapsed_time(e1) / args.steps
+    m_s, m_d = macs_per_sample(V, c["dynamic"])
+    mlp_ms = stage_ms.get("mlp_s", 0.0) + stage_ms.get("mlp_d", 0.0)
+    pk, src = peaks()
+    flops = 2.0 * (m_s + m_d) * R * S
+    achieved = flops / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
+    peak = pk["bf16_tflops_sustained"]
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "mlp_tc_kernel (2 launches/step: static + dynamic net)",
+                "peak_source": f"bf16_tflops_sustained, {src}", "mlp_ms_per_step": mlp_ms,
+                "whole_step_frac": flops / (total_ms / args.steps * 1e-3) / 1e12 / peak,
+                "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()}}
+
+    # ---------------- e2e: drop-in rendering() fed from pinned host buffers, slab by slab ----------------
+    e2e = None
+    if not args.no_e2e:
+        n_slabs = 8
+        per = -(-R // n_slabs)
+        kw = sc.render_kwargs()
+        keys = ("rgb_map", "depth_map") + (("rgb_map_ref", "depth_map_ref", "rgb_map_ref_dy", "depth_map_ref_dy",
+                                             "weights_map_dd") if c["dynamic"] else ())
+        host_out = {k: torch.empty((R, 3) if "rgb" in k else (R,), dtype=torch.float32).pin_memory() for k in keys}
+        copy_stream = torch.cuda.Stream(device=dev)
+
+        def e2e_step():
+            pending = None
+            for s in range(n_slabs):
+                a, b = s * per, min(R, (s + 1) * per)
+                with torch.cuda.stream(copy_stream):
+                    slab = [h[:, a:b].to(dev, non_blocking=True) for h in host]
+                    done = torch.cuda.Event(); done.record()
+                torch.cuda.current_stream().wait_event(done)
+                with torch.no_grad():
+                    ret = rendering(sc.args, slab[0], slab[1], slab[2], slab[3], **kw)
+                for k in keys:
+                    host_out[k][a:b].copy_(ret[k][0], non_blocking=True)
+                for t_ in slab:
+                    t_.record_stream(torch.cuda.current_stream())
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_e2e = max(2, args.steps // 2)
+        e0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e1.record()
+        barrier()
+        t_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        h2d = sum(h.numel() * 4 for h in host)
+        d2h = sum(v.numel() * 4 for v in host_out.values())
+        e2e = {"value": world * R * n_e2e / (float(t_e2e) * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": n_e2e, "api": "zest_nerf_b200.renderer.rendering, 8 slabs/frame, pinned host rays"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, sample = cpu_reference(args.config, 4096, 2)
+        cpu = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {"metric": "rays_per_sec_128_samples", "value": value, "unit": "rays/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.mlp == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": args.config + ": " + c["desc"], "rays_per_gpu_per_step": R, "samples_per_ray": S,
+                           "l2": "256 MiB buffer written between timed steps (L2 flush); per-step working set 3.6 GB > L2",
+                           "parallelism": f"ray-sharded x{world}, one NCCL frame broadcast per step" if world > 1 else "1 GPU"},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,172 @@
+/*
+ * zest_b200.h -- C ABI of the B200-native ZeST-NeRF per-ray rendering path.
+ *
+ * The reference (violetamenendez/zest-nerf) is pure Python on stock PyTorch ops; it has no
+ * FFI of its own.  This header is the boundary a maintainer binds with ctypes (see
+ * INTEGRATION.md) to replace, stage by stage, the PyTorch calls on the hot path:
+ *
+ *   zest_pack_volume / zest_pack_images   layout repack done once per frame (no reference
+ *                                         counterpart: grid_sample reads NCDHW / NCHW directly)
+ *   zest_gather_fwd / _bwd                utils.py:433-459 index_point_feature (grid_sample 3-D)
+ *                                         + utils.py:461-505 build_color_volume (grid_sample 2-D,
+ *                                         projection utils.py:257-269) + renderer.py:51-72
+ *   zest_dirfeat_fwd                      renderer.py:604 (cos_angle) + :34-49,256-258
+ *   zest_encode_fwd / _bwd                networks.py:48-65 Embedding + renderer.py:246-297 concat
+ *   zest_net_create / _destroy / _pack    networks.py:73-132 Renderer parameters (packed copies)
+ *   zest_mlp_fwd_f32 / zest_mlp_bwd_f32   networks.py:150-221 Renderer.forward, fp32 CUDA cores
+ *   zest_mlp_fwd_tc                       same, bf16 tcgen05/TMEM tensor cores, PE fused in prologue
+ *   zest_composite_static_fwd / _bwd      renderer.py:74-164 depth2dist + raw2alpha + raw2outputs
+ *   zest_composite_blend_fwd / _bwd       renderer.py:166-219 raw2outputs_blending
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer into memory owned by the caller (PyTorch); the library
+ *     never frees or retains caller memory past a call.  The only library-owned state is the
+ *     opaque zest_net handle (packed weights).
+ *   - All entry points are asynchronous on the cudaStream_t passed in (as void*), perform no
+ *     hidden synchronisation and keep no global mutable state except the last-error string.
+ *   - Return value: 0 = ok, negative = error (ZEST_E_*); zest_last_error() gives the message of
+ *     the last failure on the calling thread.  The Python wrapper raises RuntimeError.
+ *   - M = number of samples (rays * samples-per-ray), row-major [M, C] tensors unless stated.
+ *   - There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef ZEST_B200_H
+#define ZEST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZEST_OK 0
+#define ZEST_E_ARG (-1)      /* bad argument / unsupported shape */
+#define ZEST_E_CUDA (-2)     /* a CUDA runtime call or launch failed */
+#define ZEST_E_STATE (-3)    /* handle not packed / wrong net kind */
+
+typedef struct zest_net zest_net; /* opaque: packed parameters of one radiance MLP */
+
+const char* zest_last_error(void);
+int zest_version(void);
+
+/* ---- layout repack (once per frame) ------------------------------------------------------ */
+/* NCDHW fp32 [C=8, D, H, W] -> channels-last [D, H, W, 8] fp32 (one 32-byte sector per voxel). */
+int zest_pack_volume(const float* vol_ncdhw, float* vol_cl, int D, int H, int W, void* stream);
+/* [V, 3, H, W] fp32 -> [V, H, W, 4] fp32 (r,g,b,0): one 128-bit load per bilinear corner. */
+int zest_pack_images(const float* img_nchw, float* img_cl, int V, int H, int W, void* stream);
+/* gradient of zest_pack_volume: channels-last grad -> NCDHW grad (accumulates: dst += src). */
+int zest_unpack_volume_grad(const float* gvol_cl, float* gvol_ncdhw, int D, int H, int W, void* stream);
+
+/* ---- fused feature gather ---------------------------------------------------------------- */
+/* cams: [V, 24] fp32 per view: w2c rows 0..2 (12 floats, row-major 3x4), K (9 floats), 3 pad.
+ * M = R * S samples (R rays, S samples per ray; the kernel maps lanes to rays, warps to samples).
+ * feats [M, ldf]: cols 0..7 trilinear(vol, ndc), cols 8+4v.. = (r,g,b,mask) of view v.
+ * ndc has row stride ndc_ld floats (3, or 4 when a time channel is interleaved).
+ * vol_cl may be NULL (colour only) and img_cl may be NULL (volume only).
+ * vox_idx (optional, [M,3] int32: floor(ix,iy,iz)) and pix_idx (optional, [M,V,2] int32:
+ * floor of the border-clipped (ix,iy)) expose the integer indices for bit-exact parity tests. */
+int zest_gather_fwd(const float* rays_pts, const float* rays_ndc, int ndc_ld, int64_t R, int S,
+                    const float* vol_cl, int D, int Hv, int Wv,
+                    const float* img_cl, int V, int H, int W, const float* cams,
+                    float* feats, int ldf, int32_t* vox_idx, int32_t* pix_idx, void* stream);
+/* backward of the trilinear part: gfeats[M, ldf] cols 0..7 -> gvol_cl (atomic scatter-add, may be
+ * NULL) and gndc [M, gndc_ld] (d/d ndc through the interpolation weights, may be NULL; written,
+ * not accumulated).  Images and world points are data: no gradient. */
+int zest_gather_bwd(const float* rays_ndc, int ndc_ld, int64_t M, const float* vol_cl,
+                    int D, int Hv, int Wv, const float* gfeats, int ldf,
+                    float* gvol_cl, float* gndc, int gndc_ld, void* stream);
+
+/* ---- direction feature ------------------------------------------------------------------- */
+/* per ray: c = |d|, dirs = (d / c) @ R^T with R = w2c_ref[:3,:3] (row-major 3x3 passed as the
+ * first 12-float block of a cams row).  cos_angle [R], dirs [R,3]. */
+int zest_dirfeat_fwd(const float* rays_dir, int64_t R, const float* cam_ref, float* cos_angle,
+                     float* dirs, void* stream);
+
+/* ---- positional encoding + input assembly (fp32 path / module boundary) ------------------ */
+/* x [M, ldx] = [ PE_{nf_pts}(pts[M, c_pts (+ time t appended if has_t)]) | feats[M, F] |
+ *               PE_{nf_dir}(dirs[ray of row]) ], ray of row = row / S. */
+int zest_encode_fwd(const float* ndc, int ndc_ld, int has_t, float t, int nf_pts,
+                    const float* feats, int ldf, int F, const float* dirs, int nf_dir, int S,
+                    int64_t M, float* x, int ldx, void* stream);
+/* gndc[M, gndc_ld] (+)= d loss / d ndc through PE(pts) given gx[M, ldx] (first 3 channels only). */
+int zest_encode_bwd(const float* ndc, int ndc_ld, int has_t, float t, int nf_pts, const float* gx,
+                    int ldx, int64_t M, float* gndc, int gndc_ld, int accumulate, void* stream);
+
+/* ---- radiance MLP ------------------------------------------------------------------------ */
+/* kind: 0 = plain (4 outputs), 1 = static + scene-flow (5: rgb,sigma,blend_w),
+ *       2 = dynamic (12: rgb,sigma,sf_prev3,sf_post3,prob_prev,prob_post). */
+zest_net* zest_net_create(int kind, int in_pts, int in_feat, int in_views, int width, int depth,
+                          int skip);
+void zest_net_destroy(zest_net* net);
+int zest_net_out_channels(const zest_net* net);
+int zest_net_num_params(const zest_net* net);
+/* params: device pointers to fp32 tensors in nn.Linear layout ([out,in] weight, [out] bias), in
+ * this order: pts_linears[0..depth-1] (w,b each), pts_bias (w,b), feature_linear, alpha_linear,
+ * views_linears[0], rgb_linear, then kind 1: w_linear; kind 2: sf_linear, prob_linear.
+ * Builds the packed fp32 and bf16 (UMMA smem-image) copies the kernels read. */
+int zest_net_pack(zest_net* net, const float* const* params, int n_params, void* stream);
+
+/* workspace size in bytes for M rows of the fp32 path (forward; `train` keeps activations). */
+int64_t zest_mlp_f32_workspace(const zest_net* net, int64_t M, int train);
+/* x [M, ldx] assembled input (pe | feat | views) -> raw [M, out_ch] fp32. */
+int zest_mlp_fwd_f32(const zest_net* net, const float* x, int ldx, int64_t M, float* raw,
+                     void* workspace, int train, void* stream);
+/* backward given the forward's workspace (train=1): graw [M,out_ch] -> gx [M, ldx] (may be NULL)
+ * and gparams (same order/shape as params; accumulated, fp32). */
+int zest_mlp_bwd_f32(const zest_net* net, const float* x, int ldx, int64_t M, const float* graw,
+                     void* workspace, float* gx, float* const* gparams, int n_params,
+                     void* stream);
+
+/* bf16 tensor-core path (tcgen05.mma, fp32 accumulate in TMEM).  PE fused in the prologue:
+ * inputs are the un-encoded ndc (+ constant t), the gathered feats and the per-ray dirs. */
+int zest_mlp_fwd_tc(const zest_net* net, const float* ndc, int ndc_ld, int has_t, float t,
+                    const float* feats, int ldf, const float* dirs, int S, int64_t M, float* raw,
+                    void* stream);
+/* same kernel fed with an already assembled x (module boundary MVSNeRF.forward(x)). */
+int zest_mlp_fwd_tc_x(const zest_net* net, const float* x, int ldx, int64_t M, float* raw,
+                      void* stream);
+
+/* ---- alpha compositing (warp per ray) ---------------------------------------------------- */
+/* raw [R*S, ld_raw] (rgb_raw 3, sigma_raw 1, ...), z [R,S], cos_angle [R], noise [R,S] or NULL
+ * (already scaled by raw_noise_std).  Outputs: rgb_map [R,3], depth_map [R], acc [R] (optional),
+ * weights [R,S] (optional), alpha [R,S] (optional).  t_stop > 0 enables the early-termination
+ * mask: once transmittance < t_stop the remaining samples are skipped except the tail sample
+ * (whose dist is 1e10); 0 reproduces the reference exactly. */
+int zest_composite_static_fwd(const float* raw, int ld_raw, const float* z, const float* cos_angle,
+                              const float* noise, int64_t R, int S, int white_bkgd, float t_stop,
+                              float* rgb_map, float* depth_map, float* acc, float* weights,
+                              float* alpha, void* stream);
+int zest_composite_static_bwd(const float* raw, int ld_raw, const float* z, const float* cos_angle,
+                              const float* noise, int64_t R, int S, int white_bkgd,
+                              const float* g_rgb_map, const float* g_depth_map,
+                              const float* g_weights, const float* g_alpha, float* g_raw,
+                              int ld_graw, void* stream);
+/* blended static+dynamic composite.  raw_dy [R*S, ld_dy], raw_rig [R*S, ld_rig] (blend weight b
+ * in column 4 of raw_rig, already sigmoid-ed by the net). Outputs: rgb_map_ref [R,3],
+ * depth_map_ref [R], rgb_map_ref_dy [R,3], depth_map_ref_dy [R], weights_map_dd [R],
+ * weights_ref_dy [R,S] (optional, the dynamic-only weights). */
+int zest_composite_blend_fwd(const float* raw_dy, int ld_dy, const float* raw_rig, int ld_rig,
+                             const float* z, const float* cos_angle, const float* noise, int64_t R,
+                             int S, float t_stop, float* rgb_map, float* depth_map, float* rgb_map_dy,
+                             float* depth_map_dy, float* weights_dd, float* weights_dy,
+                             void* stream);
+int zest_composite_blend_bwd(const float* raw_dy, int ld_dy, const float* raw_rig, int ld_rig,
+                             const float* z, const float* cos_angle, const float* noise, int64_t R,
+                             int S, const float* g_rgb_map, const float* g_depth_map,
+                             const float* g_rgb_map_dy, const float* g_depth_map_dy,
+                             const float* g_weights_dy, float* g_raw_dy, int ld_gdy,
+                             float* g_raw_rig, int ld_grig, void* stream);
+
+/* ---- diagnostics -------------------------------------------------------------------------- */
+/* Runs D[128,N] = A[128,K] * B[N,K]^T through the tcgen05 path with the library's own smem
+ * layouts (A, B bf16 row-major in global; D fp32 row-major).  Unit-test hook for the UMMA
+ * descriptors; N multiple of 16 <= 256, K multiple of 16 <= 256.  variant 0 = the layout the
+ * library uses; 1 = LBO/SBO swapped (diagnostic only, expected to fail). */
+int zest_tc_selftest(const uint16_t* A, const uint16_t* B, float* D, int N, int K, int variant,
+                     void* stream);
+/* How many kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t zest_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZEST_B200_H */

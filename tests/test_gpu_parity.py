@@ -1,0 +1,351 @@
+"""GPU parity tests: every CUDA stage, called through the C ABI, against the CPU oracle and the
+committed golden vectors (which are outputs of the real reference).
+
+Bars (BASELINE.json north_star): voxel / pixel indices bit-exact; RGB / depth <= 2e-3 max-abs with
+the fp32 MLP; PSNR delta <= 0.05 dB with the bf16 tensor-core MLP.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import zest_oracle as zo
+from tests.helpers import CASES, build_case, load_golden, psnr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def zops(lib):
+    from zest_nerf_b200 import ops
+    assert torch.cuda.is_available()
+    return ops
+
+
+def to_dev(sc, rays):
+    sc.to(DEV)
+    return {k: v.to(DEV) for k, v in rays.items()}
+
+
+# ----------------------------------------------------------------------------- tcgen05 layout
+@pytest.mark.parametrize("N,K", [(16, 16), (16, 256), (128, 64), (128, 256), (256, 32), (256, 256)])
+def test_tc_selftest_umma_layout(zops, lib, N, K):
+    import ctypes as C
+    g = torch.Generator().manual_seed(N * 1000 + K)
+    A = (torch.randn((128, K), generator=g)).to(torch.bfloat16).to(DEV)
+    B = (torch.randn((N, K), generator=g)).to(torch.bfloat16).to(DEV)
+    want = A.float() @ B.float().t()
+    res = {}
+    for variant in (0, 1):
+        D = torch.zeros((128, N), device=DEV)
+        rc = lib.zest_tc_selftest(C.c_void_p(A.data_ptr()), C.c_void_p(B.data_ptr()), C.c_void_p(D.data_ptr()), N, K,
+                                  variant, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, lib.zest_last_error()
+        torch.cuda.synchronize()
+        res[variant] = float((D - want).abs().max())
+    assert res[0] <= 1e-2 * max(1.0, K ** 0.5), f"UMMA layout mismatch: variant errors {res}"
+
+
+# ----------------------------------------------------------------------------- gather
+def _gather_case(zops, name):
+    sc, rays, mode, _ = build_case(name)
+    R, S = rays["rays_pts"].shape[1:3]
+    (x0, y0, z0), _, _ = zo.trilinear_corners(sc.vol_static.shape, rays["rays_ndc"])
+    feats_cpu, pix_cpu = zo.colour_features(rays["rays_pts"], sc.im_cam_mat, sc.imgs[:, :-1], return_idx=True)
+    vol_cpu = zo.trilinear_sample(sc.vol_static, rays["rays_ndc"])
+    d = to_dev(sc, rays)
+    vol_cl, img_cl = zops.pack_volume(sc.vol_static), zops.pack_images(sc.imgs[:, :-1].contiguous())
+    cams = zops.cam_table(sc.im_cam_mat, sc.V)
+    F = 8 + 4 * sc.V
+    feats, vox, pix = zops.gather_fwd(d["rays_pts"].reshape(-1, 3).contiguous(), d["rays_ndc"].reshape(-1, 3).contiguous(),
+                                      vol_cl, img_cl, cams, R, S, F, want_idx=True)
+    torch.cuda.synchronize()
+    return (x0, y0, z0), pix_cpu, torch.cat([vol_cpu, feats_cpu], -1), feats.cpu(), vox.cpu(), pix.cpu(), R, S
+
+
+@pytest.mark.parametrize("name", ["static_val", "dynamic_val_v10", "train_fwd"])
+def test_gather_indices_bit_exact_and_values(zops, name):
+    (x0, y0, z0), pix_cpu, feats_cpu, feats, vox, pix, R, S = _gather_case(zops, name)
+    want_vox = torch.stack([x0, y0, z0], -1).reshape(-1, 3).int()
+    assert torch.equal(vox, want_vox), f"voxel corner mismatch in {(vox != want_vox).any(-1).sum()} samples"
+    want_pix = pix_cpu.reshape(R * S, -1, 2).int()
+    assert torch.equal(pix, want_pix), f"pixel corner mismatch in {(pix != want_pix).any(-1).sum()} samples"
+    assert float((feats - feats_cpu.reshape(R * S, -1)).abs().max()) <= 1e-5
+
+
+def test_gather_edge_cases(zops):
+    """ndc exactly on voxel corners, far outside the volume, points behind a camera, non-finite."""
+    sc, rays, _, _ = build_case("static_val")
+    D, Hv, Wv = sc.vol_static.shape[2:]
+    g = torch.Generator().manual_seed(9)
+    R, S = 8, 32
+    ndc = torch.rand((1, R, S, 3), generator=g)
+    ndc[0, 0] = torch.stack([torch.randint(0, Wv, (S,), generator=g) / (Wv - 1),
+                             torch.randint(0, Hv, (S,), generator=g) / (Hv - 1),
+                             torch.randint(0, D, (S,), generator=g) / (D - 1)], -1)   # integer voxel coords
+    ndc[0, 1] = ndc[0, 1] * 4 - 2        # mostly outside
+    ndc[0, 2, :4] = torch.tensor([0.0, 1.0, -0.0, 1.0 + 1e-7]).view(4, 1)
+    ndc[0, 3, 0] = float("inf")
+    ndc[0, 3, 1] = float("nan")
+    pts = (torch.rand((1, R, S, 3), generator=g) - 0.5) * 12   # some behind the cameras
+    pts[0, 4, :, 2] = -3.0
+    (x0, y0, z0), _, _ = zo.trilinear_corners(sc.vol_static.shape, ndc)
+    vol_cpu = zo.trilinear_sample(sc.vol_static, ndc, fast=True)
+    col_cpu, pix_cpu = zo.colour_features(pts, sc.im_cam_mat, sc.imgs[:, :-1], return_idx=True)
+    col_fast = zo.colour_features(pts, sc.im_cam_mat, sc.imgs[:, :-1], fast=True)
+    sc.to(DEV)
+    feats, vox, pix = zops.gather_fwd(pts.to(DEV).reshape(-1, 3).contiguous(), ndc.to(DEV).reshape(-1, 3).contiguous(),
+                                      zops.pack_volume(sc.vol_static), zops.pack_images(sc.imgs[:, :-1].contiguous()),
+                                      zops.cam_table(sc.im_cam_mat, sc.V), R, S, 8 + 4 * sc.V, want_idx=True)
+    feats, vox, pix = feats.cpu().view(1, R, S, -1), vox.cpu().view(1, R, S, 3), pix.cpu()
+    finite = torch.isfinite(ndc).all(-1)
+    want_vox = torch.stack([x0, y0, z0], -1).int()
+    assert torch.equal(vox[finite], want_vox[finite])
+    assert float((feats[..., :8][finite] - vol_cpu[finite]).abs().max()) <= 1e-5
+    assert float(feats[..., :8][~finite].abs().max()) == 0.0          # ATen: non-finite -> -100 -> zero padding
+    ok = torch.isfinite(col_fast).all(-1)
+    assert torch.equal(pix.view(1, R, S, -1, 2)[ok], pix_cpu.int()[ok])
+    assert float((feats[..., 8:][ok] - col_fast[ok]).abs().max()) <= 1e-5
+    assert float((col_cpu[ok] - col_fast[ok]).abs().max()) <= 1e-5
+
+
+# ----------------------------------------------------------------------------- encode / MLP
+def test_encode_matches_oracle(zops):
+    g = torch.Generator().manual_seed(1)
+    M, S = 4096, 64
+    ndc = torch.rand((M, 3), generator=g) * 1.4 - 0.2
+    feats = torch.randn((M, 20), generator=g)
+    dirs = torch.randn((M // S, 3), generator=g)
+    want = torch.cat([zo.pos_enc(ndc, 10), feats, zo.pos_enc(dirs.repeat_interleave(S, 0), 4)], -1)
+    got = zops.encode_fwd(ndc.to(DEV), None, 10, feats.to(DEV), dirs.to(DEV), 4, S).cpu()
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 2e-6
+    t = 0.1
+    want_t = zo.pos_enc(torch.cat([ndc, torch.full((M, 1), t)], -1), 10)
+    got_t = zops.encode_fwd(ndc.to(DEV), t, 10, feats.to(DEV), dirs.to(DEV), 4, S).cpu()[:, :84]
+    assert float((got_t - want_t).abs().max()) <= 2e-6
+
+
+def _rand_x(sc, net, M, seed):
+    g = torch.Generator().manual_seed(seed)
+    nerf = net.nerf
+    pts = torch.rand((M, 4 if nerf.in_ch_pts == 84 else 3), generator=g)
+    x = torch.cat([zo.pos_enc(pts, 10), torch.randn((M, nerf.in_ch_feat), generator=g) * 0.5,
+                   zo.pos_enc(torch.nn.functional.normalize(torch.randn((M, 3), generator=g), dim=-1), 4)], -1)
+    return x
+
+
+@pytest.mark.parametrize("which", ["static", "dynamic"])
+def test_mlp_fp32_matches_oracle(zops, which):
+    sc, _, _, _ = build_case("dynamic_val")
+    net = sc.net_static if which == "static" else sc.net_dynamic
+    x = _rand_x(sc, net, 1000, 3)          # not a multiple of the 128-row tile
+    with torch.no_grad():
+        want = zo.mlp_forward(net.nerf, x)
+        net.to(DEV)
+        with zops.mlp_mode("fp32"):
+            got = net(x.to(DEV)).cpu()
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 1e-4
+
+
+@pytest.mark.parametrize("which", ["static", "dynamic"])
+def test_mlp_tensor_core_matches_oracle_to_bf16_accuracy(zops, which):
+    sc, _, _, _ = build_case("dynamic_val")
+    net = sc.net_static if which == "static" else sc.net_dynamic
+    x = _rand_x(sc, net, 128 * 5 + 37, 4)
+    with torch.no_grad():
+        want = zo.mlp_forward(net.nerf, x)
+        net.to(DEV)
+        with zops.mlp_mode("bf16"):
+            got = net(x.to(DEV)).cpu()
+    assert got.shape == want.shape and torch.isfinite(got).all()
+    err = float((got - want).abs().max())
+    scale = float(want.abs().max())
+    assert err <= 3e-2 * max(scale, 1.0), f"bf16 MLP max|err| {err:.3e} (scale {scale:.2f})"
+    # and it must be a real bf16-level match, not a coincidence of scale
+    rel = float(((got - want) ** 2).sum().sqrt() / (want ** 2).sum().sqrt())
+    assert rel <= 2e-2, rel
+
+
+# ----------------------------------------------------------------------------- composite
+def test_composite_kernels_match_oracle(zops):
+    g = torch.Generator().manual_seed(2)
+    for R, S in ((37, 128), (5, 64), (3, 50)):
+        raw_s = torch.randn((1, R, S, 5), generator=g)
+        raw_s[..., 4] = torch.rand((1, R, S), generator=g)
+        raw_d = torch.randn((1, R, S, 12), generator=g)
+        raw_s[0, 0, :, 3] = -1.0      # empty ray
+        raw_s[0, 1, :, 3] = 30.0      # opaque ray
+        z = torch.linspace(2, 6, S).expand(1, R, S).contiguous() + torch.rand((1, R, 1), generator=g)
+        cos = torch.rand((1, R, 1), generator=g) + 0.5
+        noise = torch.randn((1, R, S), generator=g)
+        dists = torch.cat([z[..., 1:] - z[..., :-1], torch.full((1, R, 1), 1e10)], -1) * cos
+        for wb in (False, True):
+            for nz in (None, noise):
+                w_rgb, w_depth, w_acc, w_w, w_a = zo.composite_static(raw_s[..., :4], z, dists, wb, nz)
+                rgb, depth, w, a = zops.composite_static(raw_s.view(-1, 5).to(DEV), z.view(R, S).to(DEV), cos.view(R).to(DEV),
+                                                         None if nz is None else nz.view(R, S).to(DEV), R, S, wb)
+                for got, want in ((rgb, w_rgb), (depth, w_depth), (w, w_w), (a, w_a)):
+                    assert float((got.cpu().view(want.shape) - want).abs().max()) <= 2e-5
+        want = zo.composite_blend(raw_d[..., :4], raw_s[..., :4], raw_s[..., 4], z, dists, noise)
+        got = zops.composite_blend(raw_d.view(-1, 12).to(DEV), raw_s.view(-1, 5).to(DEV), z.view(R, S).to(DEV),
+                                   cos.view(R).to(DEV), noise.view(R, S).to(DEV), R, S, want_per_sample=True)
+        want = list(want[:4]) + [want[5].sum(-1), want[4]]
+        for gt, wt in zip(got, want):
+            assert float((gt.cpu().view(wt.shape) - wt).abs().max()) <= 2e-5
+
+
+def test_early_termination_mask_error_is_bounded(zops):
+    sc, rays, mode, _ = build_case("static_val")
+    g = torch.Generator().manual_seed(3)
+    R, S = 64, 128
+    raw = torch.randn((R * S, 4), generator=g)
+    raw[:, 3] += 3.0                    # dense scene
+    z = torch.linspace(2, 6, S).expand(R, S).contiguous()
+    cos = torch.ones(R)
+    exact = zops.composite_static(raw.to(DEV), z.to(DEV), cos.to(DEV), None, R, S, False, t_stop=0.0)
+    fast = zops.composite_static(raw.to(DEV), z.to(DEV), cos.to(DEV), None, R, S, False, t_stop=1e-4)
+    assert float((exact[0] - fast[0]).abs().max()) <= 1e-4           # skipped mass <= T
+    assert float((exact[1] - fast[1]).abs().max()) <= 6e-4 + 1e-6    # x far plane
+    assert float((fast[2] == 0).float().mean()) > 0.5                # most samples were masked out
+
+
+# ----------------------------------------------------------------------------- the boundary
+def _render(zops, name, mode_name, seed_noise=True):
+    from zest_nerf_b200.renderer import rendering
+    sc, rays, mode, _ = build_case(name)
+    want, _, noise = load_golden(name)
+    d = to_dev(sc, rays)
+    with torch.no_grad(), zops.mlp_mode(mode_name):
+        got = rendering(sc.args, d["rays_pts"], d["rays_ndc"], d["depth_candidates"], d["rays_dir"],
+                        **{**sc.render_kwargs(), **mode})
+    torch.cuda.synchronize()
+    return got, want, noise
+
+
+@pytest.mark.parametrize("name", ["static_val", "dynamic_val", "dynamic_val_v10", "train_fwd", "train_fwd5"])
+def test_rendering_fp32_matches_reference_golden(zops, name):
+    got, want, _ = _render(zops, name, "fp32")
+    assert set(got) == set(want), set(got) ^ set(want)
+    for k, v in want.items():
+        if v is None:
+            assert got[k] is None
+            continue
+        assert tuple(got[k].shape) == tuple(v.shape), (k, got[k].shape, v.shape)
+        assert got[k].dtype == torch.float32 and got[k].is_cuda
+        err = float((got[k].cpu() - v).abs().max())
+        assert err <= 2e-3, f"{name}:{k} max|err| {err:.3e}"
+
+
+def test_rendering_train_keys_with_noise(zops):
+    """raw_noise_std > 0: RNG differs from the CPU reference, so check structure + quirk C1
+    (white background in the prev/post passes) via acc: rgb_map_prev_dy >= weights sum."""
+    got, want, _ = _render(zops, "train_bwd5_noise", "fp32")
+    assert set(got) == set(want)
+    for k, v in want.items():
+        assert tuple(got[k].shape) == tuple(v.shape), k
+        assert torch.isfinite(got[k]).all(), k
+
+
+@pytest.mark.parametrize("name", ["static_val", "dynamic_val", "dynamic_val_v10"])
+def test_rendering_bf16_close_to_reference(zops, name):
+    got, want, _ = _render(zops, name, "bf16")
+    for k in ("rgb_map", "rgb_map_ref", "rgb_map_ref_dy"):
+        if k in want:
+            assert float((got[k].cpu() - want[k]).abs().max()) <= 3e-2, k
+    for k in ("depth_map", "depth_map_ref"):
+        if k in want:
+            assert float((got[k].cpu() - want[k]).abs().max()) <= 0.15, k
+
+
+def test_bf16_psnr_delta_full_frame(zops):
+    """PSNR of the bf16 render vs the fp32 render against the same target image: |delta| <= 0.05 dB."""
+    from zest_nerf_b200 import rays as zrays
+    from zest_nerf_b200.renderer import rendering
+    from zest_nerf_b200.synthetic import make_scene
+    sc = make_scene(H=64, W=80, V=3, pad=24, D=128, dynamic=True, seed=21)
+    pts, rdir, ndc, z = zrays.build_rays_val(sc.H, sc.W, sc.w2cs, sc.c2ws, sc.intrinsics, sc.near_fars, 128, pad=24)
+    target = sc.imgs[0, -1].permute(1, 2, 0).reshape(-1, 3)
+    sc.to(DEV)
+    out = {}
+    with torch.no_grad():
+        for m in ("fp32", "bf16"):
+            with zops.mlp_mode(m):
+                out[m] = rendering(sc.args, pts.to(DEV), ndc.to(DEV), z.to(DEV), rdir.to(DEV), **sc.render_kwargs())
+    for k in ("rgb_map", "rgb_map_ref"):
+        p32 = psnr(out["fp32"][k][0].cpu(), target)
+        p16 = psnr(out["bf16"][k][0].cpu(), target)
+        assert abs(p32 - p16) <= 0.05, f"{k}: PSNR fp32 {p32:.4f} dB vs bf16 {p16:.4f} dB"
+        assert psnr(out["fp32"][k][0].cpu(), out["bf16"][k][0].cpu()) >= 40.0
+
+
+def test_ray_sharding_is_bit_identical(zops):
+    """No cross-ray arithmetic: rendering two slabs == rendering the whole chunk, bit for bit."""
+    from zest_nerf_b200.renderer import rendering
+    sc, rays, mode, _ = build_case("dynamic_val")
+    d = to_dev(sc, rays)
+    R = d["rays_pts"].shape[1]
+    with torch.no_grad():
+        full = rendering(sc.args, d["rays_pts"], d["rays_ndc"], d["depth_candidates"], d["rays_dir"], **{**sc.render_kwargs(), **mode})
+        parts = [rendering(sc.args, d["rays_pts"][:, a:b], d["rays_ndc"][:, a:b], d["depth_candidates"][:, a:b],
+                           d["rays_dir"][:, a:b], **{**sc.render_kwargs(), **mode}) for a, b in ((0, R // 3), (R // 3, R))]
+    for k in ("rgb_map", "depth_map", "rgb_map_ref", "depth_map_ref", "weights_map_dd"):
+        assert torch.equal(full[k], torch.cat([p[k] for p in parts], 1)), k
+
+
+def test_unsupported_modes_raise(zops):
+    from zest_nerf_b200.renderer import rendering
+    sc, rays, mode, _ = build_case("static_val")
+    d = to_dev(sc, rays)
+    kw = sc.render_kwargs()
+    with pytest.raises(NotImplementedError):
+        rendering(sc.args, d["rays_pts"], d["rays_ndc"], d["depth_candidates"], d["rays_dir"], time_codes=torch.zeros(1), **kw)
+    with pytest.raises(RuntimeError):
+        rendering(sc.args, d["rays_pts"].cpu(), d["rays_ndc"], d["depth_candidates"], d["rays_dir"], **kw)
+
+
+# ----------------------------------------------------------------------------- gradients
+@pytest.mark.parametrize("name", ["train_fwd", "train_fwd5"])
+def test_gradients_match_reference_autograd(zops, name):
+    """fine_tune.py path: d loss / d {both volumes, MLP parameters} vs autograd through the oracle."""
+    from zest_nerf_b200.renderer import rendering
+    sc, rays, mode, _ = build_case(name)
+    keys = ["rgb_map", "depth_map", "rgb_map_ref", "depth_map_ref", "rgb_map_ref_dy", "rgb_map_prev_dy", "rgb_map_post_dy",
+            "weights", "weights_ref_dy", "raw_sf_ref2prev", "raw_sf_prev2ref", "raw_pts_post", "raw_pts_pp", "prob_map_prev",
+            "raw_blend_w", "raw_prob_ref2post"] + (["rgb_map_pp_dy"] if mode["chain_5frames"] else [])
+
+    def loss_of(ret):
+        g = torch.Generator().manual_seed(99)
+        tot = 0.0
+        for k in keys:
+            w = torch.randn(ret[k].shape, generator=g).to(ret[k].device)
+            tot = tot + (ret[k] * w).sum() / ret[k].numel() ** 0.5
+        return tot
+
+    sc.vol_static.requires_grad_(True)
+    sc.vol_dynamic.requires_grad_(True)
+    ret = zo.rendering(sc.args, rays["rays_pts"], rays["rays_ndc"], rays["depth_candidates"], rays["rays_dir"],
+                       **{**sc.render_kwargs(), **mode})
+    loss_of(ret).backward()
+    want = {"vol_static": sc.vol_static.grad.clone(), "vol_dynamic": sc.vol_dynamic.grad.clone()}
+    for tag, net in (("s", sc.net_static), ("d", sc.net_dynamic)):
+        for n, p in net.named_parameters():
+            want[f"{tag}.{n}"] = p.grad.clone()
+            p.grad = None
+    sc.vol_static.grad = sc.vol_dynamic.grad = None
+    sc.vol_static = sc.vol_static.detach().to(DEV).requires_grad_(True)
+    sc.vol_dynamic = sc.vol_dynamic.detach().to(DEV).requires_grad_(True)
+    d = to_dev(sc, rays)
+    ret = rendering(sc.args, d["rays_pts"], d["rays_ndc"], d["depth_candidates"], d["rays_dir"], **{**sc.render_kwargs(), **mode})
+    loss_of(ret).backward()
+    got = {"vol_static": sc.vol_static.grad, "vol_dynamic": sc.vol_dynamic.grad}
+    for tag, net in (("s", sc.net_static), ("d", sc.net_dynamic)):
+        for n, p in net.named_parameters():
+            got[f"{tag}.{n}"] = p.grad
+    for k, w in want.items():
+        assert got[k] is not None, f"no gradient for {k}"
+        gk = got[k].cpu()
+        denom = float(w.abs().max()) + 1e-8
+        err = float((gk - w).abs().max()) / denom
+        assert err <= 2e-3, f"grad {k}: rel max err {err:.3e} (|g|max {denom:.3e})"

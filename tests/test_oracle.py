@@ -1,0 +1,63 @@
+"""CPU tests: the oracle against the committed golden vectors produced by the real reference."""
+import pytest
+import torch
+
+from oracle import zest_oracle as zo
+from tests.helpers import CASES, build_case, checksum, load_golden
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_matches_reference_golden(name):
+    sc, rays, mode, _ = build_case(name)
+    want, chk, noise = load_golden(name)
+    # the seeded inputs must be the ones the fixtures were generated from
+    for k, v in rays.items():
+        assert checksum(v) == pytest.approx(chk[k], rel=1e-12), f"input drift in {k}"
+    assert checksum(sc.vol_static) == pytest.approx(chk["vol_static"], rel=1e-12)
+    assert sum(checksum(p) for p in sc.net_static.parameters()) == pytest.approx(chk["net_static"], rel=1e-12)
+    with torch.no_grad():
+        got = zo.rendering(sc.args, rays["rays_pts"], rays["rays_ndc"], rays["depth_candidates"], rays["rays_dir"],
+                           noise=noise, **{**sc.render_kwargs(), **mode})
+    assert set(got) == set(want)
+    for k, v in want.items():
+        if v is None:
+            assert got[k] is None
+            continue
+        assert got[k].shape == v.shape and got[k].dtype == v.dtype, k
+        assert float((got[k] - v).abs().max()) <= 2e-6, k
+
+
+def test_fast_variant_equals_explicit_gathers():
+    sc, rays, mode, _ = build_case("dynamic_val")
+    with torch.no_grad():
+        a = zo.rendering(sc.args, rays["rays_pts"], rays["rays_ndc"], rays["depth_candidates"], rays["rays_dir"],
+                         **{**sc.render_kwargs(), **mode})
+        b = zo.rendering(sc.args, rays["rays_pts"], rays["rays_ndc"], rays["depth_candidates"], rays["rays_dir"],
+                         fast=True, **{**sc.render_kwargs(), **mode})
+    for k in a:
+        if a[k] is not None:
+            assert float((a[k] - b[k]).abs().max()) <= 2e-6, k
+
+
+def test_explicit_corner_indices_are_consistent_with_grid_sample():
+    """A one-hot-ish volume makes any wrong corner index a large value error."""
+    g = torch.Generator().manual_seed(5)
+    vol = torch.randint(0, 1000, (1, 8, 6, 7, 9), generator=g).float()
+    ndc = torch.rand((1, 50, 16, 3), generator=g) * 1.2 - 0.1
+    a = zo.trilinear_sample(vol, ndc)
+    b = zo.trilinear_sample(vol, ndc, fast=True)
+    assert float((a - b).abs().max()) <= 1e-3 * 1000 * 1e-3
+
+
+def test_edge_cases_zero_density_and_tail_sample():
+    """sigma = 0 everywhere -> acc = 0; sigma > 0 at the last sample -> it absorbs all transmittance."""
+    R, S = 4, 16
+    z = torch.linspace(2, 6, S).expand(1, R, S).contiguous()
+    dists = torch.cat([z[..., 1:] - z[..., :-1], torch.full((1, R, 1), 1e10)], -1)
+    raw = torch.zeros(1, R, S, 4)
+    rgb, depth, acc, w, a = zo.composite_static(raw, z, dists)
+    assert float(acc.abs().max()) == 0.0
+    raw[..., 3] = 0.5
+    rgb, depth, acc, w, a = zo.composite_static(raw, z, dists)
+    assert torch.allclose(acc, torch.ones_like(acc), atol=1e-6)
+    assert float(a[..., -1].min()) == 1.0

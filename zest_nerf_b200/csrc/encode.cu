@@ -1,0 +1,100 @@
+// Positional encoding + MLP-input assembly for the fp32 path and the module boundary.
+//
+// Replaces networks.py:48-65 (Embedding.forward) and the torch.cat chain of
+// renderer.py:246-297 (prepare_pts) / :300-318 (prepare_dynamic_pts):
+//   x[m] = [ PE_n(ndc[m] (, t)) | feats[m] | PE_d(dirs[m / S]) ]
+// Embedding layout: [v(C), sin(2^0 v)(C), cos(2^0 v)(C), sin(2^1 v)(C), ...]; 2^k * v is exact in
+// fp32, sinf/cosf are the <= 1 ulp library versions (arguments reach 512 rad: no fast intrinsics).
+// The bf16 tensor-core MLP does NOT use this kernel: it fuses the same encoding in its prologue.
+#include "common.cuh"
+
+namespace zest {
+
+__device__ __forceinline__ float pe_value(float v, int block) {
+  if (block == 0) return v;
+  const int k = (block - 1) >> 1;
+  const float a = v * (float)(1 << k);
+  return ((block - 1) & 1) ? cosf(a) : sinf(a);
+}
+
+__global__ void encode_fwd_kernel(const float* __restrict__ ndc, int ndc_ld, int has_t, float t, int nf_pts,
+                                  const float* __restrict__ feats, int ldf, int F,
+                                  const float* __restrict__ dirs, int nf_dir, int S, int64_t M,
+                                  float* __restrict__ x, int ldx) {
+  const int C = has_t ? 4 : 3;
+  const int c_pe = C * (2 * nf_pts + 1), c_dir = dirs ? 3 * (2 * nf_dir + 1) : 0;
+  const int width = c_pe + F + c_dir;
+  const int64_t total = M * width;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / width;
+    const int j = (int)(i - m * width);
+    float out;
+    if (j < c_pe) {
+      const int ch = j % C;
+      const float v = (ch == 3) ? t : __ldg(ndc + m * ndc_ld + ch);
+      out = pe_value(v, j / C);
+    } else if (j < c_pe + F) {
+      out = __ldg(feats + m * ldf + (j - c_pe));
+    } else {
+      const int jj = j - c_pe - F;
+      out = pe_value(__ldg(dirs + (m / S) * 3 + jj % 3), jj / 3);
+    }
+    x[m * ldx + j] = out;
+  }
+}
+
+// d/d ndc of PE: sum over blocks of gx * (1 | 2^k cos | -2^k sin); time channel has no gradient.
+__global__ void encode_bwd_kernel(const float* __restrict__ ndc, int ndc_ld, int has_t, int nf_pts,
+                                  const float* __restrict__ gx, int ldx, int64_t M, float* gndc, int gndc_ld,
+                                  int accumulate) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * 3) return;
+  const int64_t m = i / 3;
+  const int ch = (int)(i - m * 3);
+  const int C = has_t ? 4 : 3;
+  const float v = __ldg(ndc + m * ndc_ld + ch);
+  const float* g = gx + m * ldx;
+  float acc = __ldg(g + ch);
+  for (int k = 0; k < nf_pts; ++k) {
+    const float f = (float)(1 << k);
+    float sn, cs;
+    sincosf(v * f, &sn, &cs);
+    acc += f * (__ldg(g + C * (1 + 2 * k) + ch) * cs - __ldg(g + C * (2 + 2 * k) + ch) * sn);
+  }
+  float* o = gndc + m * gndc_ld + ch;
+  *o = accumulate ? (*o + acc) : acc;
+}
+
+}  // namespace zest
+
+using namespace zest;
+
+extern "C" int zest_encode_fwd(const float* ndc, int ndc_ld, int has_t, float t, int nf_pts, const float* feats,
+                               int ldf, int F, const float* dirs, int nf_dir, int S, int64_t M, float* x,
+                               int ldx, void* stream) {
+  ZEST_CHECK_ARG(ndc && x && M >= 0 && ndc_ld >= 3 && nf_pts >= 0 && nf_pts <= 16 && nf_dir >= 0 && nf_dir <= 16 && S > 0,
+                 "zest_encode_fwd: bad arguments");
+  ZEST_CHECK_ARG(F == 0 || (feats && ldf >= F), "zest_encode_fwd: bad feats");
+  const int width = (has_t ? 4 : 3) * (2 * nf_pts + 1) + F + (dirs ? 3 * (2 * nf_dir + 1) : 0);
+  ZEST_CHECK_ARG(ldx >= width, "zest_encode_fwd: ldx %d < row width %d", ldx, width);
+  if (M == 0) return ZEST_OK;
+  const int64_t total = M * width;
+  const int64_t blocks = (total + 255) / 256;
+  const unsigned grid = (unsigned)(blocks < (int64_t)num_sms() * 64 ? blocks : (int64_t)num_sms() * 64);
+  encode_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ndc, ndc_ld, has_t, t, nf_pts, feats, ldf, F, dirs,
+                                                            nf_dir, S, M, x, ldx);
+  ZEST_LAUNCH_CHECK();
+  return ZEST_OK;
+}
+
+extern "C" int zest_encode_bwd(const float* ndc, int ndc_ld, int has_t, float t, int nf_pts, const float* gx,
+                               int ldx, int64_t M, float* gndc, int gndc_ld, int accumulate, void* stream) {
+  (void)t;
+  ZEST_CHECK_ARG(ndc && gx && gndc && M >= 0 && ndc_ld >= 3 && gndc_ld >= 3 && nf_pts >= 0 && nf_pts <= 16,
+                 "zest_encode_bwd: bad arguments");
+  if (M == 0) return ZEST_OK;
+  encode_bwd_kernel<<<(unsigned)((M * 3 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ndc, ndc_ld, has_t, nf_pts, gx,
+                                                                                      ldx, M, gndc, gndc_ld, accumulate);
+  ZEST_LAUNCH_CHECK();
+  return ZEST_OK;
+}

@@ -1,0 +1,367 @@
+// fp32 radiance MLP (CUDA cores): forward and backward of networks.py:150-221 (Renderer.forward, v0).
+//
+// This is the precision-reference path ("fp32 MLP" of the parity bar: RGB/depth <= 2e-3 max-abs)
+// and the training path (fine_tune.py): it keeps every activation when train=1 so the backward
+// can run layer by layer.  The inference hot path is the bf16 tcgen05 kernel in mlp_tc.cu.
+//
+//   g   = pts_bias(feat)                                   networks.py:174
+//   h_i = relu(L_i(h_{i-1}) * g), i < depth; [pe | h] after layer `skip`   :176-182
+//   sigma = alpha_linear(h); feat = feature_linear(h)      :195-198
+//   v = relu(views_linears[0]([feat | dirpe])); rgb = rgb_linear(v)   :199-207
+//   static+sf: b = sigmoid(w_linear(h)); dynamic: sf = tanh(sf_linear(h)), prob = sigmoid(prob_linear(h))  :184-191
+#include <vector>
+
+#include "net.cuh"
+#include "sgemm.cuh"
+
+namespace zest {
+
+int in_layer(const zest_net* n, int layer) {
+  if (layer == 0) return n->in_pts;
+  if (layer == n->skip + 1) return n->width + n->in_pts;
+  return n->width;
+}
+
+static inline int64_t up4(int64_t v) { return (v + 3) & ~int64_t(3); }
+
+// Workspace plan: offsets in floats, every row-major [M, ld] block starts 16-byte aligned.
+struct F32Plan {
+  int W, P, F, Cv, D, skip, ns;
+  int ldX5, ldVX;
+  int64_t G, X5, H[16], Z[16], VX, V128, SH, RGB;           // forward
+  int64_t gHa, gHb, dZ, gG, gX5, gVX, gV128, gSH, gRGB;      // backward scratch (train only)
+  int64_t total;
+  F32Plan(const zest_net* n, int64_t M, bool train) {
+    W = n->width; P = n->in_pts; F = n->in_feat; Cv = n->in_views; D = n->depth; skip = n->skip; ns = n->n_small;
+    ldX5 = (int)up4(P + W); ldVX = (int)up4(W + Cv);
+    int64_t o = 0;
+    auto take = [&](int64_t per_row) { int64_t r = o; o += up4(M * per_row); return r; };
+    G = take(W); X5 = take(ldX5);
+    if (train) {
+      for (int i = 0; i < D; ++i) { H[i] = (i == skip) ? -1 : take(W); Z[i] = take(W); }
+    } else {
+      const int64_t a = take(W), b = take(W);
+      for (int i = 0; i < D; ++i) { H[i] = (i == skip) ? -1 : ((i & 1) ? b : a); Z[i] = -1; }
+    }
+    VX = take(ldVX); V128 = take(W / 2); SH = take(16); RGB = take(4);
+    if (train) {
+      gHa = take(W); gHb = take(W); dZ = take(W); gG = take(W); gX5 = take(ldX5); gVX = take(ldVX);
+      gV128 = take(W / 2); gSH = take(16); gRGB = take(4);
+    }
+    total = o;
+  }
+};
+
+__global__ void finalize_fwd_kernel(const float* __restrict__ rgb, const float* __restrict__ sh, int kind,
+                                    int64_t M, float* __restrict__ raw, int out_ch) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float* o = raw + m * out_ch;
+  o[0] = rgb[m * 4]; o[1] = rgb[m * 4 + 1]; o[2] = rgb[m * 4 + 2];
+  const float* s = sh + m * 16;
+  o[3] = s[0];
+  if (kind == 1) {
+    o[4] = 1.f / (1.f + expf(-s[1]));
+  } else if (kind == 2) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o[4 + k] = tanhf(s[1 + k]);
+    o[10] = 1.f / (1.f + expf(-s[7]));
+    o[11] = 1.f / (1.f + expf(-s[8]));
+  }
+}
+
+__global__ void finalize_bwd_kernel(const float* __restrict__ graw, const float* __restrict__ sh, int kind,
+                                    int64_t M, int out_ch, float* __restrict__ grgb, float* __restrict__ gsh) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const float* g = graw + m * out_ch;
+  const float* s = sh + m * 16;
+  grgb[m * 4] = g[0]; grgb[m * 4 + 1] = g[1]; grgb[m * 4 + 2] = g[2]; grgb[m * 4 + 3] = 0.f;
+  float* o = gsh + m * 16;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) o[k] = 0.f;
+  o[0] = g[3];
+  if (kind == 1) {
+    const float y = 1.f / (1.f + expf(-s[1]));
+    o[1] = g[4] * y * (1.f - y);
+  } else if (kind == 2) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { const float y = tanhf(s[1 + k]); o[1 + k] = g[4 + k] * (1.f - y * y); }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { const float y = 1.f / (1.f + expf(-s[7 + k])); o[7 + k] = g[10 + k] * y * (1.f - y); }
+  }
+}
+
+// dZ = gH * 1[H>0] * G ;  gG += gH * 1[H>0] * Z
+__global__ void gate_bwd_kernel(const float* __restrict__ gH, int64_t ldgh, const float* __restrict__ H, int64_t ldh,
+                                const float* __restrict__ Z, const float* __restrict__ G, int64_t M, int W,
+                                float* __restrict__ dZ, float* __restrict__ gG) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * W) return;
+  const int64_t m = i / W;
+  const int j = (int)(i - m * W);
+  const float g = (H[m * ldh + j] > 0.f) ? gH[m * ldgh + j] : 0.f;
+  dZ[i] = g * G[i];
+  gG[i] += g * Z[i];
+}
+
+__global__ void relu_mask_kernel(float* __restrict__ g, const float* __restrict__ y, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !(y[i] > 0.f)) g[i] = 0.f;
+}
+
+// out[j] += sum_m X[m*ld + j], j < J (J <= 1024).  Each block reduces a slab of rows.
+__global__ void colsum_kernel(const float* __restrict__ X, int64_t ld, int64_t M, int J, float* out) {
+  const int64_t rows_per = (M + gridDim.x - 1) / gridDim.x;
+  const int64_t m0 = blockIdx.x * rows_per, m1 = (m0 + rows_per < M) ? m0 + rows_per : M;
+  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+    float s = 0.f;
+    for (int64_t m = m0; m < m1; ++m) s += X[m * ld + j];
+    atomicAdd(out + j, s);
+  }
+}
+
+static int colsum(const float* X, int64_t ld, int64_t M, int J, float* out, cudaStream_t st) {
+  if (!out) return ZEST_OK;
+  const unsigned grid = (unsigned)((M + 511) / 512 < 1024 ? (M + 511) / 512 : 1024);
+  colsum_kernel<<<grid, 256, 0, st>>>(X, ld, M, J, out);
+  ZEST_LAUNCH_CHECK();
+  return ZEST_OK;
+}
+
+static int copy2d(float* dst, int64_t ldd, const float* src, int64_t lds, int cols, int64_t M, cudaStream_t st) {
+  if (cols <= 0 || M <= 0) return ZEST_OK;
+  ZEST_CUDA(cudaMemcpy2DAsync(dst, ldd * sizeof(float), src, lds * sizeof(float), (size_t)cols * sizeof(float),
+                              (size_t)M, cudaMemcpyDeviceToDevice, st));
+  return ZEST_OK;
+}
+
+#define ZEST_TRY(expr) do { int _r = (expr); if (_r != ZEST_OK) return _r; } while (0)
+
+// y = x @ W^T + b  with W [J, K] row-major (nn.Linear)
+static GemmArgs linear(const float* x, int64_t ldx, const float* W, int J, int64_t K, const float* b, float* y,
+                       int64_t ldy, int64_t M) {
+  GemmArgs a{};
+  a.A = x; a.sa_i = ldx; a.sa_k = 1;
+  a.B = W; a.sb_j = K; a.sb_k = 1;
+  a.C = y; a.ldc = ldy; a.I = M; a.J = J; a.K = K; a.bias = b;
+  return a;
+}
+// gx = gy @ W  with W [N, J] row-major: reduce over N
+static GemmArgs linear_bwd_x(const float* gy, int64_t ldgy, const float* W, int N, int J, float* gx, int64_t ldgx,
+                             int64_t M, int accumulate) {
+  GemmArgs a{};
+  a.A = gy; a.sa_i = ldgy; a.sa_k = 1;
+  a.B = W; a.sb_j = 1; a.sb_k = J;
+  a.C = gx; a.ldc = ldgx; a.I = M; a.J = J; a.K = N; a.accumulate = accumulate;
+  return a;
+}
+// gW [N, J] += gy^T @ x : reduce over the M rows, split across grid.z
+static GemmArgs linear_bwd_w(const float* gy, int64_t ldgy, int N, const float* x, int64_t ldx, int J, float* gW,
+                             int64_t M) {
+  GemmArgs a{};
+  a.A = gy; a.sa_i = 1; a.sa_k = ldgy;
+  a.B = x; a.sb_j = 1; a.sb_k = ldx;
+  a.C = gW; a.ldc = J; a.I = N; a.J = J; a.K = M; a.accumulate = 1;
+  int64_t s = M / 2048;
+  a.splits = (int)(s < 2 ? 2 : (s > 256 ? 256 : s));
+  return a;
+}
+
+}  // namespace zest
+
+using namespace zest;
+
+extern "C" zest_net* zest_net_create(int kind, int in_pts, int in_feat, int in_views, int width, int depth, int skip) {
+  if (kind < 0 || kind > 2 || in_pts <= 0 || in_feat <= 0 || in_views <= 0 || width <= 0 || (width & 1) ||
+      depth < 2 || depth > 16 || skip < 0 || skip >= depth - 1) {
+    set_error("zest_net_create: unsupported configuration (kind=%d in_pts=%d in_feat=%d in_views=%d width=%d depth=%d skip=%d)",
+              kind, in_pts, in_feat, in_views, width, depth, skip);
+    return nullptr;
+  }
+  zest_net* n = new zest_net();
+  n->kind = kind; n->in_pts = in_pts; n->in_feat = in_feat; n->in_views = in_views;
+  n->width = width; n->depth = depth; n->skip = skip;
+  n->out_ch = kind == 0 ? 4 : (kind == 1 ? 5 : 12);
+  n->n_small = kind == 0 ? 1 : (kind == 1 ? 2 : 9);
+  n->packed = false; n->f32 = nullptr; n->tc_blob = nullptr; n->tc_bias = nullptr; n->tc_plan_host = nullptr; n->tc_bytes = 0;
+  // blob layout; the stacked small heads keep alpha first so column 0 of SH is sigma
+  int64_t o = 0;
+  int pi = 0;
+  auto put = [&](int64_t numel) { int64_t r = o; n->param_off[pi] = o; n->param_numel[pi] = numel; ++pi; o += numel; return r; };
+  const int W = width;
+  for (int i = 0; i < depth; ++i) { n->w_pts[i] = put((int64_t)W * in_layer(n, i)); n->b_pts[i] = put(W); }
+  n->w_gate = put((int64_t)W * in_feat); n->b_gate = put(W);
+  n->w_feat = put((int64_t)W * W); n->b_feat = put(W);
+  // alpha w/b are params (2*depth+4, +5); the extra heads come last in parameter order but are
+  // laid out so that [alpha.w ; extra.w] and [alpha.b ; extra.b] are contiguous matrices.
+  const int64_t small_w = o; o += (int64_t)n->n_small * W;
+  const int64_t small_b = o; o += n->n_small;
+  n->w_small = small_w; n->b_small = small_b;
+  n->param_off[pi] = small_w; n->param_numel[pi] = W; ++pi;      // alpha_linear.weight
+  n->param_off[pi] = small_b; n->param_numel[pi] = 1; ++pi;      // alpha_linear.bias
+  n->w_views = put((int64_t)(W / 2) * (W + in_views)); n->b_views = put(W / 2);
+  n->w_rgb = put((int64_t)3 * (W / 2)); n->b_rgb = put(3);
+  if (kind == 1) {
+    n->param_off[pi] = small_w + W; n->param_numel[pi] = W; ++pi;       // w_linear.weight
+    n->param_off[pi] = small_b + 1; n->param_numel[pi] = 1; ++pi;       // w_linear.bias
+  } else if (kind == 2) {
+    n->param_off[pi] = small_w + W; n->param_numel[pi] = 6 * (int64_t)W; ++pi;       // sf_linear.weight
+    n->param_off[pi] = small_b + 1; n->param_numel[pi] = 6; ++pi;
+    n->param_off[pi] = small_w + 7 * (int64_t)W; n->param_numel[pi] = 2 * (int64_t)W; ++pi;  // prob_linear.weight
+    n->param_off[pi] = small_b + 7; n->param_numel[pi] = 2; ++pi;
+  }
+  n->n_params = pi;
+  n->f32_floats = o;
+  if (cudaMalloc(&n->f32, (size_t)o * sizeof(float)) != cudaSuccess) {
+    set_error("zest_net_create: cudaMalloc of %lld bytes failed", (long long)(o * 4));
+    delete n;
+    return nullptr;
+  }
+  return n;
+}
+
+extern "C" void zest_net_destroy(zest_net* net) {
+  if (!net) return;
+  tc_free(net);
+  if (net->f32) cudaFree(net->f32);
+  delete net;
+}
+
+extern "C" int zest_net_out_channels(const zest_net* net) { return net ? net->out_ch : ZEST_E_ARG; }
+extern "C" int zest_net_num_params(const zest_net* net) { return net ? net->n_params : ZEST_E_ARG; }
+
+extern "C" int zest_net_pack(zest_net* net, const float* const* params, int n_params, void* stream) {
+  ZEST_CHECK_ARG(net && params, "zest_net_pack: null argument");
+  ZEST_CHECK_ARG(n_params == net->n_params, "zest_net_pack: expected %d parameter tensors, got %d", net->n_params, n_params);
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < n_params; ++i) {
+    ZEST_CHECK_ARG(params[i], "zest_net_pack: parameter %d is null", i);
+    ZEST_CUDA(cudaMemcpyAsync(net->f32 + net->param_off[i], params[i], (size_t)net->param_numel[i] * sizeof(float),
+                              cudaMemcpyDeviceToDevice, st));
+  }
+  ZEST_TRY(tc_pack(net, st));
+  net->packed = true;
+  return ZEST_OK;
+}
+
+extern "C" int64_t zest_mlp_f32_workspace(const zest_net* net, int64_t M, int train) {
+  if (!net || M < 0) return ZEST_E_ARG;
+  return F32Plan(net, M, train != 0).total * (int64_t)sizeof(float);
+}
+
+extern "C" int zest_mlp_fwd_f32(const zest_net* net, const float* x, int ldx, int64_t M, float* raw, void* workspace,
+                                int train, void* stream) {
+  ZEST_CHECK_ARG(net && x && raw && workspace && M >= 0, "zest_mlp_fwd_f32: null argument");
+  if (!net->packed) { set_error("zest_mlp_fwd_f32: net not packed"); return ZEST_E_STATE; }
+  ZEST_CHECK_ARG(ldx >= net->in_pts + net->in_feat + net->in_views, "zest_mlp_fwd_f32: ldx too small");
+  if (M == 0) return ZEST_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const F32Plan p(net, M, train != 0);
+  float* ws = (float*)workspace;
+  const float* w = net->f32;
+  const int W = p.W, P = p.P;
+  float* G = ws + p.G;
+  float* X5 = ws + p.X5;
+  { GemmArgs a = linear(x + P, ldx, w + net->w_gate, W, p.F, w + net->b_gate, G, W, M); ZEST_TRY(launch_gemm(a, st)); }
+  ZEST_TRY(copy2d(X5, p.ldX5, x, ldx, P, M, st));
+  const float* in = x; int64_t ld_in = ldx;
+  for (int i = 0; i < p.D; ++i) {
+    float* out = (i == p.skip) ? X5 + P : ws + p.H[i];
+    const int64_t ld_out = (i == p.skip) ? p.ldX5 : W;
+    GemmArgs a = linear(in, ld_in, w + net->w_pts[i], W, in_layer(net, i), w + net->b_pts[i], out, ld_out, M);
+    a.gate = G; a.ldg = W; a.relu = 1;
+    if (train) { a.Z = ws + p.Z[i]; a.ldz = W; }
+    ZEST_TRY(launch_gemm(a, st));
+    if (i == p.skip) { in = X5; ld_in = p.ldX5; } else { in = out; ld_in = ld_out; }
+  }
+  float* VX = ws + p.VX; float* V128 = ws + p.V128; float* SH = ws + p.SH; float* RGB = ws + p.RGB;
+  { GemmArgs a = linear(in, ld_in, w + net->w_feat, W, W, w + net->b_feat, VX, p.ldVX, M); ZEST_TRY(launch_gemm(a, st)); }
+  ZEST_TRY(copy2d(VX + W, p.ldVX, x + P + p.F, ldx, p.Cv, M, st));
+  { GemmArgs a = linear(in, ld_in, w + net->w_small, p.ns, W, w + net->b_small, SH, 16, M); ZEST_TRY(launch_gemm(a, st)); }
+  { GemmArgs a = linear(VX, p.ldVX, w + net->w_views, W / 2, W + p.Cv, w + net->b_views, V128, W / 2, M); a.relu = 1; ZEST_TRY(launch_gemm(a, st)); }
+  { GemmArgs a = linear(V128, W / 2, w + net->w_rgb, 3, W / 2, w + net->b_rgb, RGB, 4, M); ZEST_TRY(launch_gemm(a, st)); }
+  finalize_fwd_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(RGB, SH, net->kind, M, raw, net->out_ch);
+  ZEST_LAUNCH_CHECK();
+  return ZEST_OK;
+}
+
+extern "C" int zest_mlp_bwd_f32(const zest_net* net, const float* x, int ldx, int64_t M, const float* graw,
+                                void* workspace, float* gx, float* const* gparams, int n_params, void* stream) {
+  ZEST_CHECK_ARG(net && x && graw && workspace && M >= 0, "zest_mlp_bwd_f32: null argument");
+  ZEST_CHECK_ARG(!gparams || n_params == net->n_params, "zest_mlp_bwd_f32: expected %d gradient tensors", net->n_params);
+  if (!net->packed) { set_error("zest_mlp_bwd_f32: net not packed"); return ZEST_E_STATE; }
+  if (M == 0) return ZEST_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const F32Plan p(net, M, true);
+  float* ws = (float*)workspace;
+  const float* w = net->f32;
+  const int W = p.W, P = p.P, D = p.D;
+  auto gp = [&](int idx) -> float* { return gparams ? gparams[idx] : nullptr; };
+  const int I_GATE = 2 * D, I_FEAT = 2 * D + 2, I_ALPHA = 2 * D + 4, I_VIEWS = 2 * D + 6, I_RGB = 2 * D + 8, I_EXTRA = 2 * D + 10;
+  float* G = ws + p.G; float* X5 = ws + p.X5; float* VX = ws + p.VX; float* V128 = ws + p.V128; float* SH = ws + p.SH;
+  float* gHa = ws + p.gHa; float* gHb = ws + p.gHb; float* dZ = ws + p.dZ; float* gG = ws + p.gG; float* gX5 = ws + p.gX5;
+  float* gVX = ws + p.gVX; float* gV128 = ws + p.gV128; float* gSH = ws + p.gSH; float* gRGB = ws + p.gRGB;
+  const unsigned gm = (unsigned)((M + 255) / 256);
+
+  finalize_bwd_kernel<<<gm, 256, 0, st>>>(graw, SH, net->kind, M, net->out_ch, gRGB, gSH);
+  ZEST_LAUNCH_CHECK();
+  // rgb_linear
+  if (gp(I_RGB)) { ZEST_TRY(launch_gemm(linear_bwd_w(gRGB, 4, 3, V128, W / 2, W / 2, gp(I_RGB), M), st)); ZEST_TRY(colsum(gRGB, 4, M, 3, gp(I_RGB + 1), st)); }
+  ZEST_TRY(launch_gemm(linear_bwd_x(gRGB, 4, w + net->w_rgb, 3, W / 2, gV128, W / 2, M, 0), st));
+  relu_mask_kernel<<<(unsigned)((M * (W / 2) + 255) / 256), 256, 0, st>>>(gV128, V128, M * (W / 2));
+  ZEST_LAUNCH_CHECK();
+  // views_linears[0]
+  if (gp(I_VIEWS)) { ZEST_TRY(launch_gemm(linear_bwd_w(gV128, W / 2, W / 2, VX, p.ldVX, W + p.Cv, gp(I_VIEWS), M), st)); ZEST_TRY(colsum(gV128, W / 2, M, W / 2, gp(I_VIEWS + 1), st)); }
+  ZEST_TRY(launch_gemm(linear_bwd_x(gV128, W / 2, w + net->w_views, W / 2, W + p.Cv, gVX, p.ldVX, M, 0), st));
+  // last hidden activation
+  const int last = D - 1;
+  const float* Hl = (last == p.skip) ? X5 + P : ws + p.H[last];
+  const int64_t ldHl = (last == p.skip) ? p.ldX5 : W;
+  // feature_linear and the stacked small heads feed gH of the last layer
+  if (gp(I_FEAT)) { ZEST_TRY(launch_gemm(linear_bwd_w(gVX, p.ldVX, W, Hl, ldHl, W, gp(I_FEAT), M), st)); ZEST_TRY(colsum(gVX, p.ldVX, M, W, gp(I_FEAT + 1), st)); }
+  ZEST_TRY(launch_gemm(linear_bwd_x(gVX, p.ldVX, w + net->w_feat, W, W, gHa, W, M, 0), st));
+  if (gp(I_ALPHA)) { ZEST_TRY(launch_gemm(linear_bwd_w(gSH, 16, 1, Hl, ldHl, W, gp(I_ALPHA), M), st)); ZEST_TRY(colsum(gSH, 16, M, 1, gp(I_ALPHA + 1), st)); }
+  if (net->kind == 1 && gp(I_EXTRA)) {
+    ZEST_TRY(launch_gemm(linear_bwd_w(gSH + 1, 16, 1, Hl, ldHl, W, gp(I_EXTRA), M), st)); ZEST_TRY(colsum(gSH + 1, 16, M, 1, gp(I_EXTRA + 1), st));
+  } else if (net->kind == 2 && gp(I_EXTRA)) {
+    ZEST_TRY(launch_gemm(linear_bwd_w(gSH + 1, 16, 6, Hl, ldHl, W, gp(I_EXTRA), M), st)); ZEST_TRY(colsum(gSH + 1, 16, M, 6, gp(I_EXTRA + 1), st));
+    ZEST_TRY(launch_gemm(linear_bwd_w(gSH + 7, 16, 2, Hl, ldHl, W, gp(I_EXTRA + 2), M), st)); ZEST_TRY(colsum(gSH + 7, 16, M, 2, gp(I_EXTRA + 3), st));
+  }
+  ZEST_TRY(launch_gemm(linear_bwd_x(gSH, 16, w + net->w_small, p.ns, W, gHa, W, M, 1), st));
+
+  ZEST_CUDA(cudaMemsetAsync(gG, 0, (size_t)M * W * sizeof(float), st));
+  float* gH = gHa; int64_t ldgH = W;
+  float* other = gHb;
+  bool gx_pe_written = false;
+  for (int i = D - 1; i >= 0; --i) {
+    const float* Hi = (i == p.skip) ? X5 + P : ws + p.H[i];
+    const int64_t ldHi = (i == p.skip) ? p.ldX5 : W;
+    gate_bwd_kernel<<<(unsigned)((M * W + 255) / 256), 256, 0, st>>>(gH, ldgH, Hi, ldHi, ws + p.Z[i], G, M, W, dZ, gG);
+    ZEST_LAUNCH_CHECK();
+    // layer input
+    const float* in; int64_t ld_in; const int K = in_layer(net, i);
+    if (i == 0) { in = x; ld_in = ldx; }
+    else if (i == p.skip + 1) { in = X5; ld_in = p.ldX5; }
+    else { in = (i - 1 == p.skip) ? X5 + P : ws + p.H[i - 1]; ld_in = (i - 1 == p.skip) ? p.ldX5 : W; }
+    if (gp(2 * i)) { ZEST_TRY(launch_gemm(linear_bwd_w(dZ, W, W, in, ld_in, K, gp(2 * i), M), st)); ZEST_TRY(colsum(dZ, W, M, W, gp(2 * i + 1), st)); }
+    if (i == 0) {
+      if (gx) ZEST_TRY(launch_gemm(linear_bwd_x(dZ, W, w + net->w_pts[0], W, P, gx, ldx, M, gx_pe_written ? 1 : 0), st));
+    } else if (i == p.skip + 1) {
+      ZEST_TRY(launch_gemm(linear_bwd_x(dZ, W, w + net->w_pts[i], W, K, gX5, p.ldX5, M, 0), st));
+      if (gx) { ZEST_TRY(copy2d(gx, ldx, gX5, p.ldX5, P, M, st)); gx_pe_written = true; }
+      gH = gX5 + P; ldgH = p.ldX5;
+    } else {
+      ZEST_TRY(launch_gemm(linear_bwd_x(dZ, W, w + net->w_pts[i], W, K, other, W, M, 0), st));
+      float* prev = (gH == gHa || gH == gHb) ? gH : ((other == gHa) ? gHb : gHa);
+      gH = other; ldgH = W; other = prev;
+    }
+  }
+  // gate (pts_bias)
+  if (gp(I_GATE)) { ZEST_TRY(launch_gemm(linear_bwd_w(gG, W, W, x + P, ldx, p.F, gp(I_GATE), M), st)); ZEST_TRY(colsum(gG, W, M, W, gp(I_GATE + 1), st)); }
+  if (gx) {
+    ZEST_TRY(launch_gemm(linear_bwd_x(gG, W, w + net->w_gate, W, p.F, gx + P, ldx, M, 0), st));
+    ZEST_TRY(copy2d(gx + P + p.F, ldx, gVX + W, p.ldVX, p.Cv, M, st));
+  }
+  return ZEST_OK;
+}

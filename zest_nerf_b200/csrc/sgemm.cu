@@ -1,0 +1,137 @@
+// fp32 SIMT GEMM: 128x128x8 block tile, 8x8 register micro-tile, register-prefetched smem stages.
+#include "sgemm.cuh"
+
+namespace zest {
+
+constexpr int BM = 128, BN = 128, BK = 8, TM = 8, TN = 8;
+
+// Load a [128 x 8] operand tile (rows r0.., reduction k0..) into smem as [BK][128].
+// Two thread mappings so that the 4 elements a thread fetches are contiguous in memory.
+struct TileLoader {
+  const float* base; int64_t s_row, s_k; int64_t rows, K;
+  bool k_contig;
+  __device__ __forceinline__ void fetch(int64_t r0, int64_t k0, int64_t k_end, float (&v)[4], int t) const {
+    if (k_contig) {
+      const int64_t r = r0 + (t >> 1);
+      const int64_t k = k0 + (t & 1) * 4;
+      const float* p = base + r * s_row + k;
+      if (r < rows && k + 3 < k_end && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = (r < rows && k + e < k_end) ? __ldg(p + e) : 0.f;
+      }
+    } else {
+      const int64_t k = k0 + (t >> 5);
+      const int64_t r = r0 + (t & 31) * 4;
+      const float* p = base + k * s_k + r * s_row;
+      if (k < k_end && r + 3 < rows && s_row == 1 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = (k < k_end && r + e < rows) ? __ldg(p + e * s_row) : 0.f;
+      }
+    }
+  }
+  __device__ __forceinline__ void stash(float (*s)[BM], const float (&v)[4], int t) const {
+    if (k_contig) {
+      const int r = t >> 1, k = (t & 1) * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[k + e][r] = v[e];
+    } else {
+      const int k = t >> 5, r = (t & 31) * 4;
+      *reinterpret_cast<float4*>(&s[k][r]) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+};
+
+__global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int t = threadIdx.x;
+  const int64_t i0 = (int64_t)blockIdx.x * BM;
+  const int64_t j0 = (int64_t)blockIdx.y * BN;
+  const int64_t kper = (g.K + g.splits - 1) / g.splits;
+  const int64_t kb = (int64_t)blockIdx.z * kper;
+  const int64_t ke = (kb + kper < g.K) ? kb + kper : g.K;
+  TileLoader la{g.A, g.sa_i, g.sa_k, g.I, g.K, g.sa_k == 1};
+  TileLoader lb{g.B, g.sb_j, g.sb_k, (int64_t)g.J, g.K, g.sb_k == 1};
+  const int tx = t & 15, ty = t >> 4;
+  float acc[TM][TN];
+#pragma unroll
+  for (int a = 0; a < TM; ++a)
+#pragma unroll
+    for (int b = 0; b < TN; ++b) acc[a][b] = 0.f;
+
+  float va[4], vb[4];
+  if (kb < ke) {
+    la.fetch(i0, kb, ke, va, t);
+    lb.fetch(j0, kb, ke, vb, t);
+    la.stash(As[0], va, t);
+    lb.stash(Bs[0], vb, t);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (int64_t k0 = kb; k0 < ke; k0 += BK) {
+    const bool more = k0 + BK < ke;
+    if (more) {
+      la.fetch(i0, k0 + BK, ke, va, t);
+      lb.fetch(j0, k0 + BK, ke, vb, t);
+    }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * TN]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * TN + 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int p = 0; p < TM; ++p)
+#pragma unroll
+        for (int q = 0; q < TN; ++q) acc[p][q] = fmaf(a[p], b[q], acc[p][q]);
+    }
+    if (more) {
+      la.stash(As[buf ^ 1], va, t);
+      lb.stash(Bs[buf ^ 1], vb, t);
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+
+  const bool atomic = g.splits > 1;
+#pragma unroll
+  for (int p = 0; p < TM; ++p) {
+    const int64_t i = i0 + ty * TM + p;
+    if (i >= g.I) continue;
+#pragma unroll
+    for (int q = 0; q < TN; ++q) {
+      const int64_t j = j0 + tx * TN + q;
+      if (j >= g.J) continue;
+      float v = acc[p][q];
+      if (g.bias && blockIdx.z == 0) v += __ldg(g.bias + j);
+      if (g.Z) g.Z[i * g.ldz + j] = v;
+      if (g.gate) v *= __ldg(g.gate + i * g.ldg + j);
+      if (g.relu) v = fmaxf(v, 0.f);
+      float* c = g.C + i * g.ldc + j;
+      if (atomic) atomicAdd(c, v);
+      else if (g.accumulate) *c += v;
+      else *c = v;
+    }
+  }
+}
+
+int launch_gemm(const GemmArgs& a, cudaStream_t st) {
+  ZEST_CHECK_ARG(a.A && a.B && a.C && a.I >= 0 && a.J > 0 && a.K >= 0 && a.splits >= 1, "gemm: bad arguments");
+  ZEST_CHECK_ARG(a.splits == 1 || (!a.Z && !a.gate && !a.relu), "gemm: split-K cannot fuse a non-linear epilogue");
+  if (a.I == 0) return ZEST_OK;
+  dim3 grid((unsigned)((a.I + BM - 1) / BM), (unsigned)((a.J + BN - 1) / BN), (unsigned)a.splits);
+  ZEST_CHECK_ARG(grid.y < 65536 && (a.I + BM - 1) / BM < (1ll << 31), "gemm: shape too large for one launch");
+  sgemm_kernel<<<grid, 256, 0, st>>>(a);
+  ZEST_LAUNCH_CHECK();
+  return ZEST_OK;
+}
+
+}  // namespace zest
