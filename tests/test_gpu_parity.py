@@ -35,15 +35,13 @@ def test_tc_selftest_umma_layout(zops, lib, N, K):
     A = (torch.randn((128, K), generator=g)).to(torch.bfloat16).to(DEV)
     B = (torch.randn((N, K), generator=g)).to(torch.bfloat16).to(DEV)
     want = A.float() @ B.float().t()
-    res = {}
-    for variant in (0, 1):
-        D = torch.zeros((128, N), device=DEV)
-        rc = lib.zest_tc_selftest(C.c_void_p(A.data_ptr()), C.c_void_p(B.data_ptr()), C.c_void_p(D.data_ptr()), N, K,
-                                  variant, C.c_void_p(torch.cuda.current_stream().cuda_stream))
-        assert rc == 0, lib.zest_last_error()
-        torch.cuda.synchronize()
-        res[variant] = float((D - want).abs().max())
-    assert res[0] <= 1e-2 * max(1.0, K ** 0.5), f"UMMA layout mismatch: variant errors {res}"
+    D = torch.zeros((128, N), device=DEV)
+    rc = lib.zest_tc_selftest(C.c_void_p(A.data_ptr()), C.c_void_p(B.data_ptr()), C.c_void_p(D.data_ptr()), N, K, 0,
+                              C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, lib.zest_last_error()
+    torch.cuda.synchronize()
+    err = float((D - want).abs().max())
+    assert err <= 1e-2 * max(1.0, K ** 0.5), f"UMMA layout mismatch: max|err| {err}"
 
 
 # ----------------------------------------------------------------------------- gather
@@ -168,6 +166,22 @@ def test_mlp_tensor_core_matches_oracle_to_bf16_accuracy(zops, which):
     assert rel <= 2e-2, rel
 
 
+def test_mlp_tensor_core_multi_tile_persistent_loop(zops):
+    """Every CTA walks >= 3 tiles (plus a ragged tail): exercises the ring / barrier phases across tiles."""
+    sc, _, _, _ = build_case("dynamic_val")
+    for net in (sc.net_static, sc.net_dynamic):
+        x = _rand_x(sc, net, 148 * 128 * 3 + 77, 6).to(DEV)
+        net.to(DEV)
+        with torch.no_grad():
+            with zops.mlp_mode("fp32"):
+                want = net(x)
+            with zops.mlp_mode("bf16"):
+                got = net(x)
+        torch.cuda.synchronize()
+        rel = float(((got - want) ** 2).sum().sqrt() / (want ** 2).sum().sqrt())
+        assert rel <= 2e-2, rel
+
+
 # ----------------------------------------------------------------------------- composite
 def test_composite_kernels_match_oracle(zops):
     g = torch.Generator().manual_seed(2)
@@ -201,7 +215,7 @@ def test_early_termination_mask_error_is_bounded(zops):
     g = torch.Generator().manual_seed(3)
     R, S = 64, 128
     raw = torch.randn((R * S, 4), generator=g)
-    raw[:, 3] += 3.0                    # dense scene
+    raw[:, 3] += 40.0                   # dense scene: T < 1e-4 after a few samples
     z = torch.linspace(2, 6, S).expand(R, S).contiguous()
     cos = torch.ones(R)
     exact = zops.composite_static(raw.to(DEV), z.to(DEV), cos.to(DEV), None, R, S, False, t_stop=0.0)

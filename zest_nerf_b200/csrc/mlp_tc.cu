@@ -251,19 +251,29 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcParams p) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
+      // a_ready[0,1] / acc_free[0,1] complete exactly once per op (and once per prologue).  mbarrier
+      // parity waits only work if NO completion is skipped, so every op observes all four barriers:
+      // lazily before the first stage that needs them, the rest when the op's stages are issued.
+      const uint32_t dep_bar[4] = {sm.a_ready, sm.a_ready + 8, sm.acc_free, sm.acc_free + 8};
       for (int64_t it = 0; it < my_tiles; ++it) {
         int op = -1;
         uint32_t waited = 0;
+        auto observe = [&](uint32_t mask, int op_idx) {
+          const uint32_t par = (uint32_t)((it * (kOpsPerTile + 1) + op_idx) & 1);
+          for (int b = 0; b < 4; ++b)
+            if ((mask >> b) & 1) wait_bar(dep_bar[b], par, 200 + b);
+        };
         for (int s = 0; s < p.n_stages; ++s) {
           const TcStage st = s_plan[s];
-          if (st.flags & ST_OPSTART) { ++op; waited = 0; }
-          const uint32_t par = (uint32_t)((it * (kOpsPerTile + 1) + op) & 1);
+          if (st.flags & ST_OPSTART) {
+            if (op >= 0) observe(~waited & 15u, op);
+            ++op; waited = 0;
+          }
           const int part = (st.flags & ST_PART1) ? 1 : 0;
-          uint32_t need = st.need & ~waited;
-          if (need & NEED_A0) wait_bar(sm.a_ready, par, 200);
-          if (need & NEED_A1) wait_bar(sm.a_ready + 8, par, 201);
-          waited |= need & (NEED_A0 | NEED_A1);
-          if (st.need & NEED_ACC) wait_bar(sm.acc_free + 8 * part, par, 210 + part);
+          uint32_t need = (st.need & (NEED_A0 | NEED_A1)) | ((st.need & NEED_ACC) ? (4u << part) : 0u);
+          need &= ~waited;
+          observe(need, op);
+          waited |= need;
           wait_bar(sm.full + 8 * slot, phase, 220 + slot);
           ptx::tc_fence_after();
           const uint32_t n = (uint32_t)st.n_div8 * 8;
@@ -279,6 +289,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcParams p) {
           if (st.flags & ST_LAST) ptx::mma_commit(sm.acc_full + 8 * part);
           if (++slot == kStages) { slot = 0; phase ^= 1; }
         }
+        observe(~waited & 15u, op);          // the last op's dependencies
+        observe(15u, kOpsPerTile);           // and the completion of its epilogue (end of tile)
       }
     }
   } else {
