@@ -41,7 +41,7 @@ constexpr int kOpsPerTile = 13;  // GATE, L0..L7, FEAT, SMALL, VIEWS, RGB
 #define ACC_COL_OF(part) ((uint32_t)(part) * 128u)
 constexpr uint32_t GATE_COL = 256, HEAD_COL = 384, HEAD2_COL = 400;
 
-enum : uint8_t { ST_FIRST = 1, ST_LAST = 2, ST_PART1 = 4, ST_OPSTART = 8 };
+enum : uint8_t { ST_FIRST = 1, ST_LAST = 2, ST_PART1 = 4, ST_OPSTART = 8, ST_OPEND = 16 };
 enum : uint8_t { NEED_A0 = 1, NEED_A1 = 2, NEED_ACC = 4 };
 
 struct TcStage {   // 16 bytes, one ring slot's worth of weights and the MMAs that consume it
@@ -251,29 +251,29 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcParams p) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
-      // a_ready[0,1] / acc_free[0,1] complete exactly once per op (and once per prologue).  mbarrier
-      // parity waits only work if NO completion is skipped, so every op observes all four barriers:
-      // lazily before the first stage that needs them, the rest when the op's stages are issued.
+      // a_ready[0,1] / acc_free[0,1] complete exactly once per op: completion #(13 it + j) is the
+      // epilogue of op j-1 (j = 0: the tile prologue, which also stands for the previous tile's RGB
+      // epilogue).  mbarrier parity waits are only sound if the MMA warp observes EVERY completion, in
+      // order, and before the next one can happen; the next one needs this op's accumulator commit, so
+      // all pending observations are forced at the stage that carries the commit (ST_LAST / ST_OPEND).
       const uint32_t dep_bar[4] = {sm.a_ready, sm.a_ready + 8, sm.acc_free, sm.acc_free + 8};
       for (int64_t it = 0; it < my_tiles; ++it) {
         int op = -1;
         uint32_t waited = 0;
-        auto observe = [&](uint32_t mask, int op_idx) {
-          const uint32_t par = (uint32_t)((it * (kOpsPerTile + 1) + op_idx) & 1);
-          for (int b = 0; b < 4; ++b)
-            if ((mask >> b) & 1) wait_bar(dep_bar[b], par, 200 + b);
-        };
         for (int s = 0; s < p.n_stages; ++s) {
           const TcStage st = s_plan[s];
-          if (st.flags & ST_OPSTART) {
-            if (op >= 0) observe(~waited & 15u, op);
-            ++op; waited = 0;
-          }
+          if (st.flags & ST_OPSTART) { ++op; waited = 0; }
           const int part = (st.flags & ST_PART1) ? 1 : 0;
           uint32_t need = (st.need & (NEED_A0 | NEED_A1)) | ((st.need & NEED_ACC) ? (4u << part) : 0u);
+          if (st.flags & ST_LAST) need |= (1u << part) | (4u << part);
+          if (st.flags & ST_OPEND) need |= 15u;
           need &= ~waited;
-          observe(need, op);
-          waited |= need;
+          if (need) {
+            const uint32_t par = (uint32_t)((it * kOpsPerTile + op) & 1);
+            for (int b = 0; b < 4; ++b)
+              if ((need >> b) & 1) wait_bar(dep_bar[b], par, 200 + b);
+            waited |= need;
+          }
           wait_bar(sm.full + 8 * slot, phase, 220 + slot);
           ptx::tc_fence_after();
           const uint32_t n = (uint32_t)st.n_div8 * 8;
@@ -289,8 +289,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcParams p) {
           if (st.flags & ST_LAST) ptx::mma_commit(sm.acc_full + 8 * part);
           if (++slot == kStages) { slot = 0; phase ^= 1; }
         }
-        observe(~waited & 15u, op);          // the last op's dependencies
-        observe(15u, kOpsPerTile);           // and the completion of its epilogue (end of tile)
       }
     }
   } else {
@@ -424,8 +422,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcParams p) {
         }
         ptx::tc_fence_before();
       }
-      arrive_idle(sm.acc_free, sm.a_ready, lane);
-      arrive_idle(sm.acc_free + 8, sm.a_ready + 8, lane);
+      // no arrival here: the next tile's prologue arrival doubles as "RGB epilogue done"
     }
   }
   ptx::tc_fence_before();
@@ -589,6 +586,8 @@ int tc_pack(zest_net* net, cudaStream_t st) {
   // RGB (N = 16) from v (A1[:, 0:128])
   add_group(0, 16, 3, HEAD2_COL, net->w_rgb, W / 2, 0, {Seg{1, 0, W / 2, 0, W / 2}}, true, need_all);
 
+  for (size_t i = 0; i < stages.size(); ++i)
+    if (i + 1 == stages.size() || (stages[i + 1].flags & ST_OPSTART)) stages[i].flags |= ST_OPEND;
   ZEST_CHECK_ARG((int)stages.size() <= kMaxPlan, "tc_pack: plan too long (%d stages)", (int)stages.size());
   ph->stages = stages; ph->n_stages = (int)stages.size();
   // bias table
