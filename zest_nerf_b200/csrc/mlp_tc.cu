@@ -70,7 +70,7 @@ struct TcPlanHost {
 };
 
 struct TcParams {
-  const TcStage* plan; int n_stages;
+  TcStage plan[kMaxPlan]; int n_stages;  // by value: lives in the constant bank -> uniform loads in the issue loop
   const uint8_t* blob;
   const float* bias;
   int bias_off[kOpsPerTile];
@@ -200,9 +200,8 @@ __device__ __forceinline__ void arrive_idle(uint32_t bar_free, uint32_t bar_read
 }
 
 template <int C>  // C = 3 (static: xyz) or 4 (dynamic: xyz + t)
-__global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ TcStage s_plan[kMaxPlan];
   __shared__ __align__(8) uint64_t s_bars[2 * kStages + 6];
   __shared__ uint32_t s_tmem;
 
@@ -216,7 +215,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcParams p) {
   sm.full = bars; sm.empty = bars + 8 * kStages; sm.acc_full = bars + 16 * kStages;
   sm.acc_free = sm.acc_full + 16; sm.a_ready = sm.acc_free + 16;
 
-  for (int i = tid; i < p.n_stages * 4; i += kThreads) reinterpret_cast<uint32_t*>(s_plan)[i] = reinterpret_cast<const uint32_t*>(p.plan)[i];
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { ptx::mbar_init(sm.full + 8 * s, 1); ptx::mbar_init(sm.empty + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) {
@@ -235,60 +233,77 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const TcParams p) {
 
   if (warp == kEpiWarps) {
     // ===================== weight producer =====================
-    if (lane == 0) {
-      uint32_t slot = 0, phase = 0;
-      for (int64_t it = 0; it < my_tiles; ++it) {
-        for (int s = 0; s < p.n_stages; ++s) {
-          const TcStage st = s_plan[s];
-          wait_bar(sm.empty + 8 * slot, phase ^ 1, 100 + slot);
-          ptx::mbar_arrive_expect_tx(sm.full + 8 * slot, st.bytes);
-          ptx::bulk_g2s(sm.ring + slot * kStageBytes, p.blob + st.src_off, st.bytes, sm.full + 8 * slot);
-          if (++slot == kStages) { slot = 0; phase ^= 1; }
+    // The whole warp runs the loop convergently (so addresses stay in uniform registers); one elected
+    // lane arms the barrier and issues the bulk copy.
+    uint32_t slot = 0, phase = 0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      for (int s = 0; s < p.n_stages; ++s) {
+        const uint32_t bytes = p.plan[s].bytes, src_off = p.plan[s].src_off;
+        wait_bar(sm.empty + 8 * slot, phase ^ 1, 100 + slot);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(sm.full + 8 * slot, bytes);
+          ptx::bulk_g2s(sm.ring + slot * kStageBytes, p.blob + src_off, bytes, sm.full + 8 * slot);
         }
+        __syncwarp();
+        if (++slot == kStages) { slot = 0; phase ^= 1; }
       }
     }
   } else if (warp == kEpiWarps + 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      uint32_t slot = 0, phase = 0;
-      // a_ready[0,1] / acc_free[0,1] complete exactly once per op: completion #(13 it + j) is the
-      // epilogue of op j-1 (j = 0: the tile prologue, which also stands for the previous tile's RGB
-      // epilogue).  mbarrier parity waits are only sound if the MMA warp observes EVERY completion, in
-      // order, and before the next one can happen; the next one needs this op's accumulator commit, so
-      // all pending observations are forced at the stage that carries the commit (ST_LAST / ST_OPEND).
-      const uint32_t dep_bar[4] = {sm.a_ready, sm.a_ready + 8, sm.acc_free, sm.acc_free + 8};
-      for (int64_t it = 0; it < my_tiles; ++it) {
-        int op = -1;
-        uint32_t waited = 0;
-        for (int s = 0; s < p.n_stages; ++s) {
-          const TcStage st = s_plan[s];
-          if (st.flags & ST_OPSTART) { ++op; waited = 0; }
-          const int part = (st.flags & ST_PART1) ? 1 : 0;
-          uint32_t need = (st.need & (NEED_A0 | NEED_A1)) | ((st.need & NEED_ACC) ? (4u << part) : 0u);
-          if (st.flags & ST_LAST) need |= (1u << part) | (4u << part);
-          if (st.flags & ST_OPEND) need |= 15u;
-          need &= ~waited;
-          if (need) {
-            const uint32_t par = (uint32_t)((it * kOpsPerTile + op) & 1);
-            for (int b = 0; b < 4; ++b)
-              if ((need >> b) & 1) wait_bar(dep_bar[b], par, 200 + b);
-            waited |= need;
-          }
-          wait_bar(sm.full + 8 * slot, phase, 220 + slot);
-          ptx::tc_fence_after();
-          const uint32_t n = (uint32_t)st.n_div8 * 8;
-          const uint32_t idesc = ptx::idesc_bf16((int)n);
-          const uint32_t a_base = (st.a_buf == 2 ? sm.s : sm.a[st.a_buf]) + st.a_chunk * kChunkBytes;
-          const uint32_t b_base = sm.ring + slot * kStageBytes;
-          for (int k = 0; k < st.n_k16; ++k) {
-            const uint64_t ad = ptx::smem_desc(a_base + k * 2 * kChunkBytes, kChunkBytes, 128);
-            const uint64_t bd = ptx::smem_desc(b_base + k * 2 * n * 16, n * 16, 128);
-            ptx::mma_bf16_ss(tmem + st.d_col, ad, bd, idesc, ((st.flags & ST_FIRST) && k == 0) ? 0u : 1u);
+    // a_ready[0,1] / acc_free[0,1] complete exactly once per op: completion #(13 it + j) is the
+    // epilogue of op j-1 (j = 0: the tile prologue, which also stands for the previous tile's RGB
+    // epilogue).  mbarrier parity waits are only sound if the MMA warp observes EVERY completion, in
+    // order, and before the next one can happen; the next one needs this op's accumulator commit, so
+    // all pending observations are forced at the stage that carries the commit (ST_LAST / ST_OPEND).
+    // The loop is warp-convergent and reads the plan from the constant bank so that the descriptor
+    // arithmetic stays on the uniform datapath; one elected lane issues the MMAs and the commits.
+    uint32_t slot = 0, phase = 0;
+    constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);           // SBO = 128 B, descriptor version 1
+    constexpr uint32_t kALo = ((uint32_t)kChunkBytes >> 4) << 16;    // LBO(A) = 128 rows * 16 B
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      int op = -1;
+      uint32_t waited = 0;
+      for (int s = 0; s < p.n_stages; ++s) {
+        const uint32_t flags = p.plan[s].flags;
+        if (flags & ST_OPSTART) { ++op; waited = 0; }
+        const uint32_t part = (flags & ST_PART1) ? 1u : 0u;
+        uint32_t need = (p.plan[s].need & (NEED_A0 | NEED_A1)) | ((p.plan[s].need & NEED_ACC) ? (4u << part) : 0u);
+        if (flags & ST_LAST) need |= (1u << part) | (4u << part);
+        if (flags & ST_OPEND) need |= 15u;
+        need &= ~waited;
+        if (need) {
+          const uint32_t par = (uint32_t)((it * kOpsPerTile + op) & 1);
+          if (need & 1u) wait_bar(sm.a_ready, par, 200);
+          if (need & 2u) wait_bar(sm.a_ready + 8, par, 201);
+          if (need & 4u) wait_bar(sm.acc_free, par, 202);
+          if (need & 8u) wait_bar(sm.acc_free + 8, par, 203);
+          waited |= need;
+        }
+        wait_bar(sm.full + 8 * slot, phase, 220 + slot);
+        ptx::tc_fence_after();
+        const uint32_t n = (uint32_t)p.plan[s].n_div8 * 8;
+        const uint32_t idesc = ptx::idesc_bf16((int)n);
+        const uint32_t a_buf = p.plan[s].a_buf;
+        const uint32_t a_addr = (a_buf == 2 ? sm.s : (a_buf == 1 ? sm.a[1] : sm.a[0])) + p.plan[s].a_chunk * kChunkBytes;
+        const uint32_t b_addr = sm.ring + slot * kStageBytes;
+        // descriptor low words; one K = 16 step advances A by 2 chunks (4096 B) and B by 2 * n * 16 B
+        uint32_t a_lo = ((a_addr >> 4) & 0x3FFF) | kALo;
+        uint32_t b_lo = ((b_addr >> 4) & 0x3FFF) | (n << 16);
+        const uint32_t d_tmem = tmem + p.plan[s].d_col;
+        const int n_k16 = p.plan[s].n_k16;
+        if (ptx::elect_one()) {
+          uint32_t acc = (flags & ST_FIRST) ? 0u : 1u;
+          for (int k = 0; k < n_k16; ++k) {
+            ptx::mma_bf16_ss(d_tmem, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, idesc, acc);
+            acc = 1u;
+            a_lo += (2u * kChunkBytes) >> 4;
+            b_lo += 2u * n;
           }
           ptx::mma_commit(sm.empty + 8 * slot);
-          if (st.flags & ST_LAST) ptx::mma_commit(sm.acc_full + 8 * part);
-          if (++slot == kStages) { slot = 0; phase ^= 1; }
+          if (flags & ST_LAST) ptx::mma_commit(sm.acc_full + 8 * part);
         }
+        __syncwarp();
+        if (++slot == kStages) { slot = 0; phase ^= 1; }
       }
     }
   } else {
@@ -635,7 +650,7 @@ static int tc_launch(const zest_net* net, TcParams& p, cudaStream_t st) {
     return ZEST_E_ARG;
   }
   const TcPlanHost* ph = (const TcPlanHost*)net->tc_plan_host;
-  p.plan = ph->d_stages; p.n_stages = ph->n_stages; p.blob = (const uint8_t*)net->tc_blob; p.bias = net->tc_bias;
+  memcpy(p.plan, ph->stages.data(), ph->stages.size() * sizeof(TcStage)); p.n_stages = ph->n_stages; p.blob = (const uint8_t*)net->tc_blob; p.bias = net->tc_bias;
   memcpy(p.bias_off, ph->bias_off, sizeof(p.bias_off));
   p.P = ph->P; p.Ppad = ph->Ppad; p.F = ph->F; p.Fpad = ph->Fpad; p.Cv = net->in_views; p.nf_pts = 10; p.nf_dir = 4;
   p.kind = net->kind; p.out_ch = net->out_ch;
