@@ -10,9 +10,12 @@
 //   VIEWS/RGB  relu(views([feat | dirpe])) -> rgb_linear (N = 16 MMA) -> raw[M, out_ch] fp32
 //
 // Warp roles (320 threads): warps 0-7 epilogue (TMEM lane quarter = warp % 4, column half = warp / 4),
-// warp 8 = weight producer (cp.async.bulk / UBLKCP into a 4-stage 16 KB ring, weights pre-packed on
+// warp 8 = weight producer (cp.async.bulk / UBLKCP into a 3-stage 20 KB ring, weights pre-packed on
 // the host side of the ABI in the exact smem image, consumption order), warp 9 = MMA issuer (one
-// elected thread) and TMEM owner.  Operand layout: K-major, no swizzle: [K/8][rows][8 x bf16], so an
+// lane walks a table of pre-built descriptor records in shared memory) and TMEM owner.
+// Biases ride in the MMA: the last weight stage of every accumulator group carries one extra K = 16
+// block whose first two columns hold the bias split into bf16 hi + lo, multiplied against a constant
+// "ones" A chunk, so the epilogue is multiply-by-gate / relu / pack only (packed f32x2 / bf16x2 ops).  Operand layout: K-major, no swizzle: [K/8][rows][8 x bf16], so an
 // epilogue thread (= one row) writes 16-byte chunks that are contiguous across the warp
 // (conflict-free) and the UMMA descriptor is LBO = rows*16 B (K direction), SBO = 128 B.
 //
@@ -30,18 +33,18 @@
 namespace zest {
 
 constexpr int kTile = 128;
-constexpr int kStageBytes = 16384;
-constexpr int kStages = 4;
+constexpr int kStageBytes = 20480;       // 16 KB of weights (N = 128 x K = 64) + 4 KB bias block
+constexpr int kStages = 3;
 constexpr int kABytes = 65536;           // one 128 x 256 bf16 activation tile
 constexpr int kChunkBytes = kTile * 16;  // one 8-column k-chunk of a 128-row tile
 constexpr int kMaxPlan = 96;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 32 * (kEpiWarps + 2);
-constexpr int kOpsPerTile = 13;  // GATE, L0..L7, FEAT, SMALL, VIEWS, RGB
+// ops per tile: GATE, L0..L7, FEAT, SMALL, VIEWS, RGB (13)
 #define ACC_COL_OF(part) ((uint32_t)(part) * 128u)
 constexpr uint32_t GATE_COL = 256, HEAD_COL = 384, HEAD2_COL = 400;
 
-enum : uint8_t { ST_FIRST = 1, ST_LAST = 2, ST_PART1 = 4, ST_OPSTART = 8, ST_OPEND = 16 };
+enum : uint8_t { ST_FIRST = 1, ST_LAST = 2, ST_PART1 = 4, ST_OPSTART = 8, ST_OPEND = 16, ST_BIAS = 32 };
 enum : uint8_t { NEED_A0 = 1, NEED_A1 = 2, NEED_ACC = 4 };
 
 struct TcStage {   // 16 bytes, one ring slot's worth of weights and the MMAs that consume it
@@ -53,50 +56,44 @@ struct TcStage {   // 16 bytes, one ring slot's worth of weights and the MMAs th
   uint8_t n_k16;     // K = 16 steps
   uint8_t n_div8;    // N / 8
   uint8_t flags;
-  uint8_t need;
+  uint8_t need;      // barrier completions the MMA warp must observe before this stage (de-duplicated per op):
+                     // bit0 a_ready[0], bit1 a_ready[1], bit2 acc_free[0], bit3 acc_free[1]
 };
 
 struct PackDesc {  // how to build one stage image from the fp32 blob
   int64_t src_off; int src_ld; int row0; int rows_valid; int col0; int cols_valid; int N; int K; int64_t dst_off;
+  int64_t bias_src;  // >= 0: append a K = 16 block [n][0] = bf16 hi, [n][1] = bf16 lo of bias[row0 + n]
 };
 
 struct TcPlanHost {
   std::vector<TcStage> stages;
-  TcStage* d_stages = nullptr;
   int n_stages = 0;
-  int P, Ppad, F, Fpad, C, nf_pts, s_chunks;
-  int bias_off[kOpsPerTile];
+  int P, Ppad, F, Fpad, C, nf_pts, s_chunks, overlap;
   size_t smem_bytes;
 };
 
 struct TcParams {
   TcStage plan[kMaxPlan]; int n_stages;  // by value: lives in the constant bank -> uniform loads in the issue loop
   const uint8_t* blob;
-  const float* bias;
-  int bias_off[kOpsPerTile];
   // inputs (fused mode) or x (x mode)
   const float* ndc; int ndc_ld; int has_t; float t;
   const float* feats; int ldf;
   const float* dirs; int S;
   const float* x; int ldx;
   int P, Ppad, F, Fpad, Cv, nf_pts, nf_dir;
-  int kind, out_ch;
+  int kind, out_ch, overlap;
   int64_t M; int64_t n_tiles;
   float* raw;
 };
 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, int tag) {
+  if (ptx::mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
-  long long t0 = 0;
   while (!ptx::mbar_try_wait(bar, parity)) {
-    if ((++spins & 0xfff) == 0) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ll) {  // ~2 s: a protocol bug must not hang the GPU
-        printf("zest mlp_tc: barrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
-        __trap();
-      }
+    if (++spins > (1u << 24)) {  // a protocol bug must not hang the GPU (each try_wait suspends for a while)
+      printf("zest mlp_tc: barrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
+      __trap();
     }
   }
 }
@@ -133,20 +130,19 @@ __device__ __forceinline__ void store_row_chunks(uint32_t buf, int chunk0, int r
 
 struct Smem {
   uint32_t a[2];      // activation tiles A0, A1
-  uint32_t s;         // PE | dirPE tile
+  uint32_t s;         // PE | dirPE | ones tile
   uint32_t ring;      // weight ring
   uint32_t full, empty, acc_full, acc_free, a_ready;  // barrier arrays
 };
 
-// ---- epilogue of one accumulator part of a hidden-type op --------------------------------------
-// MODE 0: (acc + b) * gate, relu -> bf16 A tile      (L0..L7)
-// MODE 1: acc + b -> bf16 A tile                      (FEAT)
-// MODE 2: acc + b, relu -> bf16 A tile                (VIEWS)
-// MODE 3: acc + b -> bf16 pairs into the TMEM gate    (GATE)
+// ---- epilogue of one accumulator part of a hidden-type op (bias already inside the accumulator) ----
+// MODE 0: acc * gate, relu -> bf16 A tile      (L0..L7)
+// MODE 1: acc -> bf16 A tile                    (FEAT)
+// MODE 2: acc, relu -> bf16 A tile              (VIEWS)
+// MODE 3: acc -> bf16 pairs into the TMEM gate  (GATE)
 template <int MODE>
 __device__ __forceinline__ void epilogue_part(uint32_t tmem, int part, int q, int hsel, int row, uint32_t out_buf,
-                                              const float* __restrict__ bias, uint32_t bar_free, uint32_t bar_ready,
-                                              int lane) {
+                                              uint32_t bar_free, uint32_t bar_ready, int lane) {
   const int col0 = part * 128 + hsel * 64;  // first output column of this thread
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
   uint32_t acc[2][32];
@@ -166,17 +162,15 @@ __device__ __forceinline__ void epilogue_part(uint32_t tmem, int part, int q, in
   for (int h = 0; h < 2; ++h) {
     uint32_t packed[16];
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + h * 32 + j));
-      float v0 = __uint_as_float(acc[h][j]) + b.x, v1 = __uint_as_float(acc[h][j + 1]) + b.y;
-      float v2 = __uint_as_float(acc[h][j + 2]) + b.z, v3 = __uint_as_float(acc[h][j + 3]) + b.w;
+    for (int j = 0; j < 32; j += 2) {
+      float v0 = __uint_as_float(acc[h][j]), v1 = __uint_as_float(acc[h][j + 1]);
       if (MODE == 0) {
-        const uint32_t g01 = g[h][j / 2], g23 = g[h][j / 2 + 1];
-        v0 *= ptx::bf16_lo(g01); v1 *= ptx::bf16_hi(g01); v2 *= ptx::bf16_lo(g23); v3 *= ptx::bf16_hi(g23);
+        const uint32_t g01 = g[h][j / 2];
+        ptx::mul_f32x2(v0, v1, ptx::bf16_lo(g01), ptx::bf16_hi(g01));
       }
-      if (MODE == 0 || MODE == 2) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-      packed[j / 2] = ptx::pack_bf16(v0, v1);
-      packed[j / 2 + 1] = ptx::pack_bf16(v2, v3);
+      uint32_t pk = ptx::pack_bf16(v0, v1);
+      if (MODE == 0 || MODE == 2) pk = ptx::relu_bf16x2(pk);
+      packed[j / 2] = pk;
     }
     if (MODE == 3) {
       ptx::tmem_st16(tmem + lane_addr + GATE_COL + col0 / 2 + h * 16, packed);
@@ -199,6 +193,60 @@ __device__ __forceinline__ void arrive_idle(uint32_t bar_free, uint32_t bar_read
   if (lane == 0) { ptx::mbar_arrive(bar_free); ptx::mbar_arrive(bar_ready); }
 }
 
+struct MmaCtx {
+  Smem sm;
+  uint32_t slot, phase, par, n_issued;
+  uint32_t ones_lo, ring_lo;
+  __device__ __forceinline__ void next_op() { par ^= 1u; }
+  __device__ __forceinline__ void wait(uint32_t need) {
+    if (need & 1u) wait_bar(sm.a_ready, par, 200);
+    if (need & 2u) wait_bar(sm.a_ready + 8, par, 201);
+    if (need & 4u) wait_bar(sm.acc_free, par, 202);
+    if (need & 8u) wait_bar(sm.acc_free + 8, par, 203);
+  }
+};
+
+// one ring stage: n_k16 K = 16 steps of N weight rows against the A operand starting at a_lo;
+// `last` = the accumulator group's last stage: + bias step against the ones chunk, + acc_full commit
+template <int N>
+__device__ __forceinline__ void mma_stage(MmaCtx& c, uint32_t a_lo, int n_k16, uint32_t d_tmem, bool first, bool last, int part) {
+  constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);           // SBO = 128 B, descriptor version 1
+  constexpr uint64_t kHi = (uint64_t)kDescHi << 32;
+  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+  wait_bar(c.sm.full + 8 * c.slot, c.phase, 220);
+  ptx::tc_fence_after();
+  // descriptor low words; one K = 16 step advances A by 2 chunks (4096 B) and B by 2 * N * 16 B
+  uint32_t b_lo = (c.ring_lo + c.slot * (kStageBytes >> 4)) | ((uint32_t)N << 16);
+  if (ptx::elect_one()) {
+    uint32_t acc = first ? 0u : 1u;
+    for (int k = 0; k < n_k16; ++k) {
+      ptx::mma_bf16_ss(d_tmem, kHi | a_lo, kHi | b_lo, kIdesc, acc);
+      acc = 1u;
+      a_lo += (2u * kChunkBytes) >> 4;
+      b_lo += 2u * N;
+    }
+    if (last) ptx::mma_bf16_ss(d_tmem, kHi | c.ones_lo, kHi | b_lo, kIdesc, 1u);
+    ptx::mma_commit(c.sm.empty + 8 * c.slot);
+    if (last) ptx::mma_commit(c.sm.acc_full + 8 * part);
+  }
+  __syncwarp();
+  ++c.n_issued;
+  if (++c.slot == kStages) { c.slot = 0; c.phase ^= 1u; }
+}
+
+// one K segment of an accumulator group, cut into ring stages exactly like tc_pack()'s add_group
+template <int N>
+__device__ __forceinline__ void mma_seg(MmaCtx& c, int part, uint32_t d_tmem, uint32_t a_lo, int kpad, bool first, bool last,
+                                        uint32_t need_k0, uint32_t need_k128) {
+  constexpr int kstep = (N == 16) ? 256 : 64;
+  for (int k0 = 0; k0 < kpad; k0 += kstep) {
+    const int kk = (kpad - k0 < kstep) ? kpad - k0 : kstep;
+    if (k0 == 0 && need_k0) c.wait(need_k0);
+    if (k0 == 128 && need_k128) c.wait(need_k128);
+    mma_stage<N>(c, a_lo + (uint32_t)(k0 / 8) * (kChunkBytes >> 4), kk / 16, d_tmem, first && k0 == 0, last && k0 + kk >= kpad, part);
+  }
+}
+
 template <int C>  // C = 3 (static: xyz) or 4 (dynamic: xyz + t)
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -209,11 +257,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   const uint32_t base = ptx::smem_u32(smem_raw);
   Smem sm;
   sm.a[0] = base; sm.a[1] = base + kABytes; sm.s = base + 2 * kABytes;
-  const int s_chunks = p.Ppad / 8 + 4;
+  const int ones_chunk = p.Ppad / 8 + 4;     // S = [PE (Ppad/8 chunks) | dirPE (4) | ones (2)]
+  const int s_chunks = ones_chunk + 2;
   sm.ring = sm.s + s_chunks * kChunkBytes;
   const uint32_t bars = ptx::smem_u32(s_bars);
   sm.full = bars; sm.empty = bars + 8 * kStages; sm.acc_full = bars + 16 * kStages;
   sm.acc_free = sm.acc_full + 16; sm.a_ready = sm.acc_free + 16;
+  constexpr uint32_t kALo = ((uint32_t)kChunkBytes >> 4) << 16;    // LBO(A) = 128 rows * 16 B
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { ptx::mbar_init(sm.full + 8 * s, 1); ptx::mbar_init(sm.empty + 8 * s, 1); }
@@ -224,6 +274,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     }
     ptx::fence_mbar_init();
   }
+  if (tid < kTile) {  // the constant "ones" A chunk pair: columns 0, 1 = 1.0 (bias hi, lo), the rest 0
+    ptx::st_smem_v4(sm.s + ones_chunk * kChunkBytes + tid * 16, 0x3F803F80u, 0u, 0u, 0u);
+    ptx::st_smem_v4(sm.s + (ones_chunk + 1) * kChunkBytes + tid * 16, 0u, 0u, 0u, 0u);
+    ptx::fence_proxy_async_smem();
+  }
   if (warp == kEpiWarps + 1) { ptx::tmem_alloc(ptx::smem_u32(&s_tmem), 512); ptx::tmem_relinquish(); }
   ptx::tc_fence_before();
   __syncthreads();
@@ -233,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
 
   if (warp == kEpiWarps) {
     // ===================== weight producer =====================
-    // The whole warp runs the loop convergently (so addresses stay in uniform registers); one elected
+    // The whole warp runs the loop convergently (addresses stay in uniform registers); one elected
     // lane arms the barrier and issues the bulk copy.
     uint32_t slot = 0, phase = 0;
     for (int64_t it = 0; it < my_tiles; ++it) {
@@ -253,57 +308,48 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     // a_ready[0,1] / acc_free[0,1] complete exactly once per op: completion #(13 it + j) is the
     // epilogue of op j-1 (j = 0: the tile prologue, which also stands for the previous tile's RGB
     // epilogue).  mbarrier parity waits are only sound if the MMA warp observes EVERY completion, in
-    // order, and before the next one can happen; the next one needs this op's accumulator commit, so
-    // all pending observations are forced at the stage that carries the commit (ST_LAST / ST_OPEND).
-    // The loop is warp-convergent and reads the plan from the constant bank so that the descriptor
-    // arithmetic stays on the uniform datapath; one elected lane issues the MMAs and the commits.
-    uint32_t slot = 0, phase = 0;
-    constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);           // SBO = 128 B, descriptor version 1
-    constexpr uint32_t kALo = ((uint32_t)kChunkBytes >> 4) << 16;    // LBO(A) = 128 rows * 16 B
+    // order, and before the next one can happen; every op below therefore waits on all four barriers
+    // at least once before its last commit.  The schedule is straight-line code (it must walk the
+    // ring stages in exactly the order tc_pack() laid them out; checked per tile against n_stages):
+    // the warp stays convergent, every operand is warp-uniform, one elected lane issues.
+    MmaCtx c{sm, 0u, 0u, 1u, 0u, (((sm.s + ones_chunk * kChunkBytes) >> 4) & 0x3FFF) | kALo, (sm.ring >> 4) & 0x3FFF};
+    const uint32_t s_lo = ((sm.s >> 4) & 0x3FFF) | kALo;
+    const uint32_t a_lo[2] = {((sm.a[0] >> 4) & 0x3FFF) | kALo, ((sm.a[1] >> 4) & 0x3FFF) | kALo};
+    const uint32_t dir_lo = s_lo + (p.Ppad / 8) * (kChunkBytes >> 4);
+    const uint32_t acc_t[2] = {tmem + ACC_COL_OF(0), tmem + ACC_COL_OF(1)};
+    const bool ov = p.overlap != 0;
     for (int64_t it = 0; it < my_tiles; ++it) {
-      int op = -1;
-      uint32_t waited = 0;
-      for (int s = 0; s < p.n_stages; ++s) {
-        const uint32_t flags = p.plan[s].flags;
-        if (flags & ST_OPSTART) { ++op; waited = 0; }
-        const uint32_t part = (flags & ST_PART1) ? 1u : 0u;
-        uint32_t need = (p.plan[s].need & (NEED_A0 | NEED_A1)) | ((p.plan[s].need & NEED_ACC) ? (4u << part) : 0u);
-        if (flags & ST_LAST) need |= (1u << part) | (4u << part);
-        if (flags & ST_OPEND) need |= 15u;
-        need &= ~waited;
-        if (need) {
-          const uint32_t par = (uint32_t)((it * kOpsPerTile + op) & 1);
-          if (need & 1u) wait_bar(sm.a_ready, par, 200);
-          if (need & 2u) wait_bar(sm.a_ready + 8, par, 201);
-          if (need & 4u) wait_bar(sm.acc_free, par, 202);
-          if (need & 8u) wait_bar(sm.acc_free + 8, par, 203);
-          waited |= need;
+      c.n_issued = 0;
+      // GATE: feats staged in A1 chunks [0, Fpad/8)
+      c.next_op(); c.wait(15u);
+      for (int part = 0; part < 2; ++part) mma_seg<128>(c, part, acc_t[part], a_lo[1], p.Fpad, true, true, 0u, 0u);
+      // L0: PE in S
+      c.next_op(); c.wait(15u);
+      for (int part = 0; part < 2; ++part) mma_seg<128>(c, part, acc_t[part], s_lo, p.Ppad, true, true, 0u, 0u);
+      // L1..L7 (layer l reads A[(l-1)&1]; L5 = [pe | h4]) and FEAT (l = 8: h7 in A1 -> feature)
+      for (int l = 1; l <= 8; ++l) {
+        c.next_op();
+        if (!ov) c.wait(15u);
+        const uint32_t in_lo = a_lo[(l - 1) & 1];
+        for (int part = 0; part < 2; ++part) {
+          c.wait(4u << part);
+          if (l == 5) mma_seg<128>(c, part, acc_t[part], s_lo, p.Ppad, true, false, 0u, 0u);
+          mma_seg<128>(c, part, acc_t[part], in_lo, 256, l != 5, true, part == 0 ? 1u : 0u, part == 0 ? 2u : 0u);
         }
-        wait_bar(sm.full + 8 * slot, phase, 220 + slot);
-        ptx::tc_fence_after();
-        const uint32_t n = (uint32_t)p.plan[s].n_div8 * 8;
-        const uint32_t idesc = ptx::idesc_bf16((int)n);
-        const uint32_t a_buf = p.plan[s].a_buf;
-        const uint32_t a_addr = (a_buf == 2 ? sm.s : (a_buf == 1 ? sm.a[1] : sm.a[0])) + p.plan[s].a_chunk * kChunkBytes;
-        const uint32_t b_addr = sm.ring + slot * kStageBytes;
-        // descriptor low words; one K = 16 step advances A by 2 chunks (4096 B) and B by 2 * n * 16 B
-        uint32_t a_lo = ((a_addr >> 4) & 0x3FFF) | kALo;
-        uint32_t b_lo = ((b_addr >> 4) & 0x3FFF) | (n << 16);
-        const uint32_t d_tmem = tmem + p.plan[s].d_col;
-        const int n_k16 = p.plan[s].n_k16;
-        if (ptx::elect_one()) {
-          uint32_t acc = (flags & ST_FIRST) ? 0u : 1u;
-          for (int k = 0; k < n_k16; ++k) {
-            ptx::mma_bf16_ss(d_tmem, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, idesc, acc);
-            acc = 1u;
-            a_lo += (2u * kChunkBytes) >> 4;
-            b_lo += 2u * n;
-          }
-          ptx::mma_commit(sm.empty + 8 * slot);
-          if (flags & ST_LAST) ptx::mma_commit(sm.acc_full + 8 * part);
-        }
-        __syncwarp();
-        if (++slot == kStages) { slot = 0; phase ^= 1; }
+      }
+      // SMALL heads (N = 16) from h7 (A1)
+      c.next_op(); c.wait(15u);
+      mma_seg<16>(c, 0, tmem + HEAD_COL, a_lo[1], 256, true, true, 0u, 0u);
+      // VIEWS: [feature (A0) | dirPE (S)] -> ACC0 (N = 128, single part)
+      c.next_op(); c.wait(15u);
+      mma_seg<128>(c, 0, acc_t[0], a_lo[0], 256, true, false, 0u, 0u);
+      mma_seg<128>(c, 0, acc_t[0], dir_lo, 32, false, true, 0u, 0u);
+      // RGB (N = 16) from v (A1[:, 0:128])
+      c.next_op(); c.wait(15u);
+      mma_seg<16>(c, 0, tmem + HEAD2_COL, a_lo[1], 128, true, true, 0u, 0u);
+      if (c.n_issued != (uint32_t)p.n_stages) {
+        if (lane == 0) printf("zest mlp_tc: MMA schedule walked %u stages, plan has %d\n", c.n_issued, p.n_stages);
+        __trap();
       }
     }
   } else {
@@ -370,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       for (int part = 0; part < 2; ++part) {
         wait_bar(sm.acc_full + 8 * part, nfull[part]++ & 1, 300 + part);
         ptx::tc_fence_after();
-        epilogue_part<3>(tmem, part, q, hsel, row, 0, p.bias + p.bias_off[0], sm.acc_free + 8 * part, sm.a_ready + 8 * part, lane);
+        epilogue_part<3>(tmem, part, q, hsel, row, 0, sm.acc_free + 8 * part, sm.a_ready + 8 * part, lane);
       }
       // ---- L0..L7: output ping-pongs A0, A1, ... (L0 reads S, writes A0) ----
       for (int l = 0; l < 8; ++l) {
@@ -378,14 +424,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         for (int part = 0; part < 2; ++part) {
           wait_bar(sm.acc_full + 8 * part, nfull[part]++ & 1, 310 + part);
           ptx::tc_fence_after();
-          epilogue_part<0>(tmem, part, q, hsel, row, out, p.bias + p.bias_off[1 + l], sm.acc_free + 8 * part, sm.a_ready + 8 * part, lane);
+          epilogue_part<0>(tmem, part, q, hsel, row, out, sm.acc_free + 8 * part, sm.a_ready + 8 * part, lane);
         }
       }
       // ---- FEAT: h7 (A1) -> feature (A0) ----
       for (int part = 0; part < 2; ++part) {
         wait_bar(sm.acc_full + 8 * part, nfull[part]++ & 1, 320 + part);
         ptx::tc_fence_after();
-        epilogue_part<1>(tmem, part, q, hsel, row, sm.a[0], p.bias + p.bias_off[9], sm.acc_free + 8 * part, sm.a_ready + 8 * part, lane);
+        epilogue_part<1>(tmem, part, q, hsel, row, sm.a[0], sm.acc_free + 8 * part, sm.a_ready + 8 * part, lane);
       }
       // ---- SMALL heads (N = 16): sigma + blend / scene flow / probs, kept in registers ----
       float head[12];
@@ -395,15 +441,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         uint32_t r[16];
         ptx::tmem_ld16(tmem + lane_addr + HEAD_COL, r);
         ptx::tc_wait_ld();
-        const float* b = p.bias + p.bias_off[10];
-        head[3] = __uint_as_float(r[0]) + __ldg(b);
+        head[3] = __uint_as_float(r[0]);
         if (p.kind == 1) {
-          head[4] = 1.f / (1.f + __expf(-(__uint_as_float(r[1]) + __ldg(b + 1))));
+          head[4] = 1.f / (1.f + __expf(-__uint_as_float(r[1])));
         } else if (p.kind == 2) {
 #pragma unroll
-          for (int k = 0; k < 6; ++k) head[4 + k] = tanhf(__uint_as_float(r[1 + k]) + __ldg(b + 1 + k));
+          for (int k = 0; k < 6; ++k) head[4 + k] = tanhf(__uint_as_float(r[1 + k]));
 #pragma unroll
-          for (int k = 0; k < 2; ++k) head[10 + k] = 1.f / (1.f + __expf(-(__uint_as_float(r[7 + k]) + __ldg(b + 7 + k))));
+          for (int k = 0; k < 2; ++k) head[10 + k] = 1.f / (1.f + __expf(-__uint_as_float(r[7 + k])));
         }
         ptx::tc_fence_before();
       }
@@ -412,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       // ---- VIEWS: [feature (A0) | dirPE (S)] -> relu -> A1[:, 0:128] ----
       wait_bar(sm.acc_full, nfull[0]++ & 1, 340);
       ptx::tc_fence_after();
-      epilogue_part<2>(tmem, 0, q, hsel, row, sm.a[1], p.bias + p.bias_off[11], sm.acc_free, sm.a_ready, lane);
+      epilogue_part<2>(tmem, 0, q, hsel, row, sm.a[1], sm.acc_free, sm.a_ready, lane);
       arrive_idle(sm.acc_free + 8, sm.a_ready + 8, lane);
       // ---- RGB (N = 16) -> raw ----
       wait_bar(sm.acc_full, nfull[0]++ & 1, 350);
@@ -421,10 +466,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         uint32_t r[16];
         ptx::tmem_ld16(tmem + lane_addr + HEAD2_COL, r);
         ptx::tc_wait_ld();
-        const float* b = p.bias + p.bias_off[12];
-        head[0] = __uint_as_float(r[0]) + __ldg(b);
-        head[1] = __uint_as_float(r[1]) + __ldg(b + 1);
-        head[2] = __uint_as_float(r[2]) + __ldg(b + 2);
+        head[0] = __uint_as_float(r[0]);
+        head[1] = __uint_as_float(r[1]);
+        head[2] = __uint_as_float(r[2]);
         if (valid) {
           float* o = p.raw + m * p.out_ch;
           if (p.out_ch == 12) {
@@ -455,12 +499,19 @@ __global__ void tc_pack_kernel(const float* __restrict__ f32, const PackDesc* __
     if (n < d.rows_valid && k < d.cols_valid) v = f32[d.src_off + (int64_t)(d.row0 + n) * d.src_ld + d.col0 + k];
     dst[(int64_t)(k / 8) * (d.N * 8) + n * 8 + (k % 8)] = __float2bfloat16_rn(v);
   }
-}
-
-__global__ void tc_bias_kernel(const float* __restrict__ f32, const int64_t* __restrict__ src, const int* __restrict__ cnt,
-                               const int* __restrict__ dst_off, float* bias) {
-  const int o = blockIdx.x;
-  for (int i = threadIdx.x; i < cnt[o]; i += blockDim.x) bias[dst_off[o] + i] = f32[src[o] + i];
+  if (d.bias_src >= 0) {  // trailing K = 16 block: [n][0] = hi, [n][1] = lo, zeros elsewhere
+    __nv_bfloat16* bd = dst + (int64_t)d.N * d.K;
+    for (int i = threadIdx.x; i < d.N * 16; i += blockDim.x) {
+      const int n = (i >> 3) % d.N, c = (i & 7) + 8 * (i / (d.N * 8));
+      float v = 0.f;
+      if (c < 2 && n < d.rows_valid) {
+        const float b = f32[d.bias_src + d.row0 + n];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+        v = c == 0 ? __bfloat162float(hi) : b - __bfloat162float(hi);
+      }
+      bd[i] = __float2bfloat16_rn(v);
+    }
+  }
 }
 
 // ---- self test: D[128, N] = A[128, K] * B[N, K]^T through the same layouts / descriptors ---------
@@ -515,13 +566,11 @@ static inline int up(int v, int m) { return (v + m - 1) / m * m; }
 
 void tc_free(zest_net* net) {
   if (net->tc_blob) cudaFree(net->tc_blob);
-  if (net->tc_bias) cudaFree(net->tc_bias);
   if (net->tc_plan_host) {
     TcPlanHost* ph = (TcPlanHost*)net->tc_plan_host;
-    if (ph->d_stages) cudaFree(ph->d_stages);
     delete ph;
   }
-  net->tc_blob = nullptr; net->tc_bias = nullptr; net->tc_plan_host = nullptr;
+  net->tc_blob = nullptr; net->tc_plan_host = nullptr;
 }
 
 static bool tc_supported(const zest_net* n) {
@@ -537,7 +586,8 @@ int tc_pack(zest_net* net, cudaStream_t st) {
   net->tc_plan_host = ph;
   const int W = 256, P = net->in_pts, F = net->in_feat, Cv = net->in_views;
   ph->P = P; ph->Ppad = up(P, 32); ph->F = F; ph->Fpad = up(F, 16); ph->C = (P == 84) ? 4 : 3; ph->nf_pts = 10;
-  ph->s_chunks = ph->Ppad / 8 + 4;
+  ph->overlap = overlap ? 1 : 0;
+  ph->s_chunks = ph->Ppad / 8 + 6;   // PE | dirPE (4 chunks) | ones (2 chunks)
   ph->smem_bytes = 2 * kABytes + (size_t)ph->s_chunks * kChunkBytes + (size_t)kStages * kStageBytes;
   const int Ppad = ph->Ppad, Fpad = ph->Fpad, dir_chunk = Ppad / 8;
 
@@ -545,8 +595,9 @@ int tc_pack(zest_net* net, cudaStream_t st) {
   std::vector<PackDesc> packs;
   int64_t blob_off = 0;
   struct Seg { int a_buf, a_chunk, kpad, col0, cols_valid; };
-  // one accumulator group: rows [row0, row0 + N) of a weight matrix against a list of K segments
-  auto add_group = [&](int part, int N, int rows_valid, uint32_t d_col, int64_t w_off, int w_ld, int row0,
+  // one accumulator group: rows [row0, row0 + N) of a weight matrix against a list of K segments;
+  // the group's last stage also carries the bias block (consumed against the "ones" A chunk)
+  auto add_group = [&](int part, int N, int rows_valid, uint32_t d_col, int64_t w_off, int w_ld, int row0, int64_t b_off,
                        std::vector<Seg> segs, bool op_start, uint8_t need_first) {
     bool firststage = true;
     for (size_t si = 0; si < segs.size(); ++si) {
@@ -567,77 +618,75 @@ int tc_pack(zest_net* net, cudaStream_t st) {
           if (c1 > 16) s.need |= NEED_A1;
         }
         const int valid = sg.cols_valid - k0;
-        packs.push_back(PackDesc{w_off, w_ld, row0, rows_valid, sg.col0 + k0, valid < 0 ? 0 : (valid > kk ? kk : valid), N, kk, blob_off});
+        packs.push_back(PackDesc{w_off, w_ld, row0, rows_valid, sg.col0 + k0, valid < 0 ? 0 : (valid > kk ? kk : valid), N, kk, blob_off, -1});
         blob_off += s.bytes;
         stages.push_back(s);
         firststage = false;
       }
     }
-    stages.back().flags |= ST_LAST;
+    stages.back().flags |= ST_LAST | ST_BIAS;
+    stages.back().bytes += (uint32_t)(N * 16 * 2);
+    packs.back().bias_src = b_off;
+    blob_off += N * 16 * 2;
   };
   const uint8_t need_all = NEED_A0 | NEED_A1 | NEED_ACC;
   const uint8_t need_first = overlap ? (uint8_t)NEED_ACC : need_all;
-  auto two_part = [&](int64_t w_off, int w_ld, std::vector<Seg> segs, bool conservative) {
+  auto two_part = [&](int64_t w_off, int w_ld, int64_t b_off, std::vector<Seg> segs, bool conservative) {
     for (int part = 0; part < 2; ++part)
-      add_group(part, 128, 128, ACC_COL_OF(part), w_off, w_ld, part * 128, segs, part == 0,
+      add_group(part, 128, 128, ACC_COL_OF(part), w_off, w_ld, part * 128, b_off, segs, part == 0,
                 conservative ? need_all : need_first);
   };
   // GATE: feats staged in A1 chunks [0, Fpad/8)
-  two_part(net->w_gate, F, {Seg{1, 0, Fpad, 0, F}}, true);
+  two_part(net->w_gate, F, net->b_gate, {Seg{1, 0, Fpad, 0, F}}, true);
   // L0: PE in S
-  two_part(net->w_pts[0], P, {Seg{2, 0, Ppad, 0, P}}, true);
+  two_part(net->w_pts[0], P, net->b_pts[0], {Seg{2, 0, Ppad, 0, P}}, true);
   // L1..L7; layer l reads A[(l-1)&1]; L5 = [pe | h4]
   for (int l = 1; l < 8; ++l) {
     const int in_buf = (l - 1) & 1;
-    if (l == 5) two_part(net->w_pts[l], P + W, {Seg{2, 0, Ppad, 0, P}, Seg{in_buf, 0, W, P, W}}, false);
-    else two_part(net->w_pts[l], W, {Seg{in_buf, 0, W, 0, W}}, false);
+    if (l == 5) two_part(net->w_pts[l], P + W, net->b_pts[l], {Seg{2, 0, Ppad, 0, P}, Seg{in_buf, 0, W, P, W}}, false);
+    else two_part(net->w_pts[l], W, net->b_pts[l], {Seg{in_buf, 0, W, 0, W}}, false);
   }
   // FEAT: h7 is in A1 (L7 writes A[7&1]); feature -> A0
-  two_part(net->w_feat, W, {Seg{1, 0, W, 0, W}}, false);
+  two_part(net->w_feat, W, net->b_feat, {Seg{1, 0, W, 0, W}}, false);
   // SMALL heads (N = 16) from h7 (A1)
-  add_group(0, 16, net->n_small, HEAD_COL, net->w_small, W, 0, {Seg{1, 0, W, 0, W}}, true, need_all);
+  add_group(0, 16, net->n_small, HEAD_COL, net->w_small, W, 0, net->b_small, {Seg{1, 0, W, 0, W}}, true, need_all);
   // VIEWS: [feature (A0) | dirPE (S)] -> ACC0 (N = 128, single part)
-  add_group(0, 128, 128, ACC_COL_OF(0), net->w_views, W + Cv, 0, {Seg{0, 0, W, 0, W}, Seg{2, dir_chunk, 32, W, Cv}}, true, need_all);
+  add_group(0, 128, 128, ACC_COL_OF(0), net->w_views, W + Cv, 0, net->b_views, {Seg{0, 0, W, 0, W}, Seg{2, dir_chunk, 32, W, Cv}}, true, need_all);
   // RGB (N = 16) from v (A1[:, 0:128])
-  add_group(0, 16, 3, HEAD2_COL, net->w_rgb, W / 2, 0, {Seg{1, 0, W / 2, 0, W / 2}}, true, need_all);
+  add_group(0, 16, 3, HEAD2_COL, net->w_rgb, W / 2, 0, net->b_rgb, {Seg{1, 0, W / 2, 0, W / 2}}, true, need_all);
 
   for (size_t i = 0; i < stages.size(); ++i)
     if (i + 1 == stages.size() || (stages[i + 1].flags & ST_OPSTART)) stages[i].flags |= ST_OPEND;
+  // fold the observation rule (see the MMA warp) into de-duplicated per-stage wait bits
+  {
+    uint32_t waited = 0;
+    for (auto& s : stages) {
+      if (s.flags & ST_OPSTART) waited = 0;
+      const uint32_t part = (s.flags & ST_PART1) ? 1u : 0u;
+      uint32_t need = (s.need & (NEED_A0 | NEED_A1)) | ((s.need & NEED_ACC) ? (4u << part) : 0u);
+      if (s.flags & ST_LAST) need |= (1u << part) | (4u << part);
+      if (s.flags & ST_OPEND) need |= 15u;
+      need &= ~waited;
+      waited |= need;
+      s.need = (uint8_t)need;
+    }
+  }
   ZEST_CHECK_ARG((int)stages.size() <= kMaxPlan, "tc_pack: plan too long (%d stages)", (int)stages.size());
+  for (auto& s : stages) ZEST_CHECK_ARG(s.bytes <= (uint32_t)kStageBytes && (s.bytes & 15u) == 0, "tc_pack: stage of %u bytes", s.bytes);
   ph->stages = stages; ph->n_stages = (int)stages.size();
-  // bias table
-  int64_t bsrc[kOpsPerTile]; int bcnt[kOpsPerTile]; int boff[kOpsPerTile];
-  int bo = 0;
-  auto addb = [&](int op, int64_t src, int cnt, int padded) { bsrc[op] = src; bcnt[op] = cnt; boff[op] = bo; ph->bias_off[op] = bo; bo += padded; };
-  addb(0, net->b_gate, W, W);
-  for (int l = 0; l < 8; ++l) addb(1 + l, net->b_pts[l], W, W);
-  addb(9, net->b_feat, W, W);
-  addb(10, net->b_small, net->n_small, 16);
-  addb(11, net->b_views, W / 2, W / 2);
-  addb(12, net->b_rgb, 3, 16);
 
   if (first) {
     ZEST_CUDA(cudaMalloc(&net->tc_blob, (size_t)blob_off));
-    ZEST_CUDA(cudaMalloc(&net->tc_bias, (size_t)bo * sizeof(float)));
-    ZEST_CUDA(cudaMalloc(&ph->d_stages, stages.size() * sizeof(TcStage)));
     net->tc_bytes = blob_off;
   }
-  // device-side scratch for the descriptors (freed after the pack kernels are enqueued + synced)
-  PackDesc* d_packs = nullptr; int64_t* d_bsrc = nullptr; int* d_bcnt = nullptr; int* d_boff = nullptr;
+  // device-side scratch for the descriptors (freed after the pack kernel is enqueued + synced)
+  PackDesc* d_packs = nullptr;
   ZEST_CUDA(cudaMalloc(&d_packs, packs.size() * sizeof(PackDesc)));
-  ZEST_CUDA(cudaMalloc(&d_bsrc, sizeof(bsrc))); ZEST_CUDA(cudaMalloc(&d_bcnt, sizeof(bcnt))); ZEST_CUDA(cudaMalloc(&d_boff, sizeof(boff)));
   ZEST_CUDA(cudaMemcpyAsync(d_packs, packs.data(), packs.size() * sizeof(PackDesc), cudaMemcpyHostToDevice, st));
-  ZEST_CUDA(cudaMemcpyAsync(d_bsrc, bsrc, sizeof(bsrc), cudaMemcpyHostToDevice, st));
-  ZEST_CUDA(cudaMemcpyAsync(d_bcnt, bcnt, sizeof(bcnt), cudaMemcpyHostToDevice, st));
-  ZEST_CUDA(cudaMemcpyAsync(d_boff, boff, sizeof(boff), cudaMemcpyHostToDevice, st));
-  ZEST_CUDA(cudaMemcpyAsync(ph->d_stages, stages.data(), stages.size() * sizeof(TcStage), cudaMemcpyHostToDevice, st));
-  ZEST_CUDA(cudaMemsetAsync(net->tc_bias, 0, (size_t)bo * sizeof(float), st));
   tc_pack_kernel<<<(unsigned)packs.size(), 256, 0, st>>>(net->f32, d_packs, (uint8_t*)net->tc_blob);
   ZEST_LAUNCH_CHECK();
-  tc_bias_kernel<<<kOpsPerTile, 256, 0, st>>>(net->f32, d_bsrc, d_bcnt, d_boff, net->tc_bias);
-  ZEST_LAUNCH_CHECK();
-  ZEST_CUDA(cudaStreamSynchronize(st));  // host vectors / scratch are released below
-  cudaFree(d_packs); cudaFree(d_bsrc); cudaFree(d_bcnt); cudaFree(d_boff);
+  ZEST_CUDA(cudaStreamSynchronize(st));  // host vector / scratch are released below
+  cudaFree(d_packs);
   return ZEST_OK;
 }
 
@@ -650,10 +699,9 @@ static int tc_launch(const zest_net* net, TcParams& p, cudaStream_t st) {
     return ZEST_E_ARG;
   }
   const TcPlanHost* ph = (const TcPlanHost*)net->tc_plan_host;
-  memcpy(p.plan, ph->stages.data(), ph->stages.size() * sizeof(TcStage)); p.n_stages = ph->n_stages; p.blob = (const uint8_t*)net->tc_blob; p.bias = net->tc_bias;
-  memcpy(p.bias_off, ph->bias_off, sizeof(p.bias_off));
+  memcpy(p.plan, ph->stages.data(), ph->stages.size() * sizeof(TcStage)); p.n_stages = ph->n_stages; p.blob = (const uint8_t*)net->tc_blob;
   p.P = ph->P; p.Ppad = ph->Ppad; p.F = ph->F; p.Fpad = ph->Fpad; p.Cv = net->in_views; p.nf_pts = 10; p.nf_dir = 4;
-  p.kind = net->kind; p.out_ch = net->out_ch;
+  p.kind = net->kind; p.out_ch = net->out_ch; p.overlap = ph->overlap;
   p.n_tiles = (p.M + kTile - 1) / kTile;
   if (p.M == 0) return ZEST_OK;
   const int grid = (int)(p.n_tiles < num_sms() ? p.n_tiles : num_sms());

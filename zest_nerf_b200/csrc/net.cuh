@@ -27,7 +27,6 @@ struct zest_net {
   // ---- bf16 tensor-core image (built by mlp_tc.cu) ----
   void* tc_blob;       // device: weight stages in UMMA smem-image order
   int64_t tc_bytes;
-  float* tc_bias;      // device: fp32 biases in the order the epilogue consumes them
   void* tc_plan_host;  // host: layer plan (opaque to everything but mlp_tc.cu)
 };
 
