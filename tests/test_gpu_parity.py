@@ -44,6 +44,24 @@ def test_tc_selftest_umma_layout(zops, lib, N, K):
     assert err <= 1e-2 * max(1.0, K ** 0.5), f"UMMA layout mismatch: max|err| {err}"
 
 
+@pytest.mark.parametrize("N,K", [(16, 32), (16, 256), (128, 128), (128, 256), (256, 64)])
+def test_tc_selftest_a_operand_in_tmem(zops, lib, N, K):
+    """TS-form tcgen05.mma: A written to TMEM with tcgen05.st as bf16 pairs, the way the epilogue
+    leaves the layer activation for the next layer."""
+    import ctypes as C
+    g = torch.Generator().manual_seed(N * 1000 + K + 7)
+    A = (torch.randn((128, K), generator=g)).to(torch.bfloat16).to(DEV)
+    B = (torch.randn((N, K), generator=g)).to(torch.bfloat16).to(DEV)
+    want = A.float() @ B.float().t()
+    D = torch.zeros((128, N), device=DEV)
+    rc = lib.zest_tc_selftest(C.c_void_p(A.data_ptr()), C.c_void_p(B.data_ptr()), C.c_void_p(D.data_ptr()), N, K, 1,
+                              C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, lib.zest_last_error()
+    torch.cuda.synchronize()
+    err = float((D - want).abs().max())
+    assert err <= 1e-2 * max(1.0, K ** 0.5), f"TMEM A-operand layout mismatch: max|err| {err}"
+
+
 # ----------------------------------------------------------------------------- gather
 def _gather_case(zops, name):
     sc, rays, mode, _ = build_case(name)
