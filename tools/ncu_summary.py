@@ -38,3 +38,30 @@ for i in sorted(sorted(range(len(data)), key=lambda i: -int(data[i][iS]))[:40]):
     r = data[i]
     st = sorted(((int(r[c]), hdr[c][6:]) for c in stall), reverse=True)[:2]
     print(f"  {i:6d} {int(r[iS]):8d} {100*int(r[iS])/tot:5.1f}% exec {r[iEx]:>10s}  {r[iSrc].strip()[:70]:70s} {st}")
+
+# ---- barrier-wait attribution: wait_bar(bar, parity, tag) leaves `tag` as an immediate right after its spin loop
+import re
+TAGS = {100: "producer: empty[slot]", 200: "mma: a_ready[0]", 201: "mma: a_ready[1]", 202: "mma: acc_free[0]", 203: "mma: acc_free[1]",
+        220: "mma: full[slot]", 230: "mma: full[slot] (skip)", 300: "epi GATE acc_full", 310: "epi L acc_full[0]", 311: "epi L acc_full[1]",
+        320: "epi FEAT acc_full[0]", 321: "epi FEAT acc_full[1]", 340: "epi VIEWS acc_full", 350: "epi RGB acc_full"}
+waits = collections.Counter()
+i = 0
+while i < len(data):
+    if "TRYWAIT" in data[i][iSrc]:
+        n, j = 0, i
+        while j < len(data):   # the wait shows up on the branch that consumes the try_wait predicate
+            n += int(data[j][iS])
+            if "BRA" in data[j][iSrc]:
+                break
+            j += 1
+        tag = None
+        for j in range(i + 1, min(i + 30, len(data))):
+            m = re.search(r"(?:MOV|IMAD\.MOV\.U32) R\d+, (?:RZ, RZ, )?0x([0-9a-f]+) ;?$", data[j][iSrc].strip().rstrip(";").strip() + " ;")
+            if m and 100 <= int(m.group(1), 16) <= 400:
+                tag = int(m.group(1), 16); break
+        key = tag - (tag % 10 if tag and 100 <= tag < 110 or tag and 220 <= tag < 240 else 0) if tag else None
+        waits[key] += n
+    i += 1
+print("\n  barrier-wait samples by site (share of all samples; one fully-waiting warp = %.1f%%):" % (100.0 / 10))
+for k, v in sorted(waits.items(), key=lambda x: -x[1]):
+    print(f"    {TAGS.get(k, k)!s:32s} {v:9d} {100*v/tot:5.1f}%")
