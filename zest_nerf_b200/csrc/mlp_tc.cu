@@ -16,11 +16,14 @@
 //                      alias its first 32 columns)
 //   [384,512)          the layer activation h as bf16 pairs = the A operand of the next layer's
 //                      TS-form tcgen05.mma (A from TMEM, B = weights from shared memory)
-// The activation is updated IN PLACE: the epilogue of part 0 keeps its 64 packed outputs in
-// registers until the commit of part 1 says every MMA that reads the old h has retired, then
-// stores them with tcgen05.st.  Shared memory therefore only holds the small per-tile inputs
-// (PE, dirPE, feats: SS-form MMAs) and a deep weight ring, and the MMA operand traffic out of shared
-// memory is halved.
+// The activation is updated IN PLACE.  A layer is issued as four ring stages in the order
+//   (part 0, K 0..127) (part 1, K 0..127) (part 0, K 128..255 + bias -> commit acc_full[0]) (part 1, ... -> acc_full[1])
+// so that when acc_full[0] fires every MMA that reads the low K half of the old activation has
+// retired and part 0's epilogue may overwrite exactly those columns (its outputs ARE the low K half
+// of the next layer's input); the same holds for part 1 and the high half.  The next layer's low-K
+// stages start as soon as part 0's epilogue has stored, while part 1 is still in its epilogue.
+// Shared memory therefore only holds the small per-tile inputs (PE, dirPE, feats: SS-form MMAs)
+// and a deep weight ring, and the MMA operand traffic out of shared memory is halved.
 //
 // Warp roles (320 threads): warps 0-7 prologue + epilogue (TMEM lane quarter = warp % 4, column
 // half = warp / 4), warp 8 = weight producer (cp.async.bulk / UBLKCP, weights pre-packed on the
@@ -184,20 +187,17 @@ __device__ __forceinline__ void arrive_idle(uint32_t bar_free, uint32_t bar_read
   if (lane == 0) { ptx::mbar_arrive(bar_free); ptx::mbar_arrive(bar_ready); }
 }
 
-// two-part hidden op (L0..L7): the activation is overwritten in place, so part 0's outputs
-// wait in registers for acc_full[1] (= every MMA reading the old activation has completed)
+// two-part hidden op (L0..L7): part p's outputs are K half p of the next layer's input, stored in place
 template <int MODE>
 __device__ __forceinline__ void epilogue_two_part(uint32_t tmem_lane, int hsel, const Bars& b, uint32_t (&nfull)[2], int lane) {
-  uint32_t p0[32];
-  wait_bar(b.acc_full, nfull[0]++ & 1, 310);
-  ptx::tc_fence_after();
-  epilogue_compute<MODE>(tmem_lane, 0, hsel, b.acc_free, lane, p0);
-  wait_bar(b.acc_full + 8, nfull[1]++ & 1, 311);
-  ptx::tc_fence_after();
-  epilogue_store(tmem_lane + ACT_COL + hsel * 32, p0, b.a_ready, lane);
-  uint32_t p1[32];
-  epilogue_compute<MODE>(tmem_lane, 1, hsel, b.acc_free + 8, lane, p1);
-  epilogue_store(tmem_lane + ACT_COL + 64 + hsel * 32, p1, b.a_ready + 8, lane);
+#pragma unroll
+  for (int part = 0; part < 2; ++part) {
+    uint32_t pk[32];
+    wait_bar(b.acc_full + 8 * part, nfull[part]++ & 1, 310 + part);
+    ptx::tc_fence_after();
+    epilogue_compute<MODE>(tmem_lane, part, hsel, b.acc_free + 8 * part, lane, pk);
+    epilogue_store(tmem_lane + ACT_COL + part * 64 + hsel * 32, pk, b.a_ready + 8 * part, lane);
+  }
 }
 
 // ---- MMA issue helpers (warp-convergent; every operand warp-uniform; one elected lane issues) ------
@@ -264,9 +264,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // smem: S = [PE (Ppad/8 chunks) | dirPE (4) | ones (2) | feats (Fpad/8)] then the weight ring
+  // smem: S = [PE (Ppad/8 chunks) | dirPE x 2 (4 + 4) | ones (2) | feats (Fpad/8)] then the weight ring.
+  // dirPE is double buffered by tile parity: it is read at the very end of a tile (VIEWS), after the
+  // next tile's inputs have been staged; PE (last read by L5) and feats (GATE) are not.
   const uint32_t s_base = ptx::smem_u32(smem_raw);
-  const int dir_chunk = p.Ppad / 8, ones_chunk = dir_chunk + 4, feat_chunk = ones_chunk + 2;
+  const int dir_chunk = p.Ppad / 8, ones_chunk = dir_chunk + 8, feat_chunk = ones_chunk + 2;
   const uint32_t ring = s_base + (feat_chunk + p.Fpad / 8) * kChunkBytes;
   const uint32_t bars = ptx::smem_u32(s_bars);
   Bars b;
@@ -328,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     // ring stages in exactly the order tc_pack() laid them out (checked per tile against n_stages).
     MmaCtx c{b, 0u, 1u, 0u, (((s_base + ones_chunk * kChunkBytes) >> 4) & 0x3FFF) | kALbo, (ring >> 4) & 0x3FFF};
     const uint32_t pe_lo = ((s_base >> 4) & 0x3FFF) | kALbo;
-    const uint32_t dir_lo = pe_lo + dir_chunk * (kChunkBytes >> 4);
+    const uint32_t dir_lo[2] = {pe_lo + dir_chunk * (kChunkBytes >> 4), pe_lo + (dir_chunk + 4) * (kChunkBytes >> 4)};
     const uint32_t feat_lo = pe_lo + feat_chunk * (kChunkBytes >> 4);
     const uint32_t acc0 = tmem + ACC_COL_OF(0), acc1 = tmem + ACC_COL_OF(1), act = tmem + ACT_COL;
     const bool ov = p.overlap != 0;
@@ -346,56 +348,62 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       c.wait(8u | 3u);
       mma_stage<128, false, 3>(c, pe_lo, nk_p, acc1, true, true, 1);
       c.end_revolution();
-      // ---- L1..L7 (L5 = [pe | h4]: two revolutions, the PE part from smem) ----
+      // ---- L1..L7: (p0, K lo) (p1, K lo) (p0, K hi) (p1, K hi); L5 = [pe | h4] starts with the PE blocks (smem) ----
       for (int l = 1; l < 8; ++l) {
         c.next_op();
         if (!ov) c.wait(15u);
-        if (l != 5) {
-          c.wait(4u | 1u);
-          mma_stage<128, true, 0>(c, act, 8, acc0, true, false, -1);
-          c.wait(2u);
-          mma_stage<128, true, 1>(c, act + 64, 8, acc0, false, true, 0);
-          c.wait(8u);
-          mma_stage<128, true, 2>(c, act, 8, acc1, true, false, -1);
-          mma_stage<128, true, 3>(c, act + 64, 8, acc1, false, true, 1);
-          c.end_revolution();
-        } else {
+        if (l == 5) {
           c.wait(4u);
           mma_stage<128, false, 0>(c, pe_lo, nk_p, acc0, true, false, -1);
+          c.wait(8u);
+          mma_stage<128, false, 1>(c, pe_lo, nk_p, acc1, true, false, -1);
           c.wait(1u);
-          mma_stage<128, true, 1>(c, act, 8, acc0, false, false, -1);
+          mma_stage<128, true, 2>(c, act, 8, acc0, false, false, -1);
+          mma_stage<128, true, 3>(c, act, 8, acc1, false, false, -1);
+          c.end_revolution();
           c.wait(2u);
-          mma_stage<128, true, 2>(c, act + 64, 8, acc0, false, true, 0);
+          mma_stage<128, true, 0>(c, act + 64, 8, acc0, false, true, 0);
+          mma_stage<128, true, 1>(c, act + 64, 8, acc1, false, true, 1);
+          mma_skip<2>(c);
           mma_skip<3>(c);
           c.end_revolution();
+        } else {
+          c.wait(4u | 1u);
+          mma_stage<128, true, 0>(c, act, 8, acc0, true, false, -1);
           c.wait(8u);
-          mma_stage<128, false, 0>(c, pe_lo, nk_p, acc1, true, false, -1);
-          mma_stage<128, true, 1>(c, act, 8, acc1, false, false, -1);
-          mma_stage<128, true, 2>(c, act + 64, 8, acc1, false, true, 1);
-          mma_skip<3>(c);
+          mma_stage<128, true, 1>(c, act, 8, acc1, true, false, -1);
+          c.wait(2u);
+          mma_stage<128, true, 2>(c, act + 64, 8, acc0, false, true, 0);
+          mma_stage<128, true, 3>(c, act + 64, 8, acc1, false, true, 1);
           c.end_revolution();
         }
       }
-      // ---- FEAT (h7 -> feature) with the N = 16 heads riding in front (same input, gate columns are dead) ----
+      // ---- FEAT (h7 -> feature); the N = 16 heads (same input; the gate columns are dead) ride behind the low-K stages ----
       c.next_op();
-      c.wait(15u);
-      mma_stage<16, true, 0>(c, act, 16, tmem + HEAD_COL, true, true, -1);
-      mma_stage<128, true, 1>(c, act, 8, acc0, true, false, -1);
-      mma_stage<128, true, 2>(c, act + 64, 8, acc0, false, true, 0);
-      mma_skip<3>(c);
+      if (!ov) c.wait(15u);
+      c.wait(4u | 1u);
+      mma_stage<128, true, 0>(c, act, 8, acc0, true, false, -1);
+      c.wait(8u);
+      mma_stage<128, true, 1>(c, act, 8, acc1, true, false, -1);
+      c.wait(2u);
+      mma_stage<16, true, 2>(c, act, 16, tmem + HEAD_COL, true, true, -1);
+      mma_stage<128, true, 3>(c, act + 64, 8, acc0, false, true, 0);
       c.end_revolution();
-      mma_stage<128, true, 0>(c, act, 8, acc1, true, false, -1);
-      mma_stage<128, true, 1>(c, act + 64, 8, acc1, false, true, 1);
+      mma_stage<128, true, 0>(c, act + 64, 8, acc1, false, true, 1);
+      // ---- VIEWS: [feature (TMEM) | dirPE (smem)] -> acc0 (N = 128, single part); RGB (N = 16) from v ----
+      c.next_op();
+      if (!ov) c.wait(15u);
+      c.wait(4u | 1u);
+      mma_stage<128, true, 1>(c, act, 8, acc0, true, false, -1);
+      c.wait(2u | 8u);
+      mma_stage<128, true, 2>(c, act + 64, 8, acc0, false, false, -1);
+      mma_stage<128, false, 3>(c, dir_lo[it & 1], 2, acc0, false, true, 0);
+      c.end_revolution();
+      c.next_op(); c.wait(15u);
+      mma_stage<16, true, 0>(c, act, 8, tmem + HEAD2_COL, true, true, 0);
+      mma_skip<1>(c);
       mma_skip<2>(c);
       mma_skip<3>(c);
-      c.end_revolution();
-      // ---- VIEWS: [feature (TMEM) | dirPE (smem)] -> acc0 (N = 128, single part); RGB (N = 16) from v ----
-      c.next_op(); c.wait(15u);
-      mma_stage<128, true, 0>(c, act, 8, acc0, true, false, -1);
-      mma_stage<128, true, 1>(c, act + 64, 8, acc0, false, false, -1);
-      mma_stage<128, false, 2>(c, dir_lo, 2, acc0, false, true, 0);
-      c.next_op(); c.wait(15u);
-      mma_stage<16, true, 3>(c, act, 8, tmem + HEAD2_COL, true, true, 0);
       c.end_revolution();
       if (c.n_issued != (uint32_t)p.n_stages) {
         if (lane == 0) printf("zest mlp_tc: MMA schedule walked %u stages, plan has %d\n", c.n_issued, p.n_stages);
@@ -408,11 +416,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     const int row = q * 32 + lane;
     uint32_t nfull[2] = {0, 0};
     const uint32_t tmem_lane = tmem + ((uint32_t)(q * 32) << 16);
-    for (int64_t it = 0; it < my_tiles; ++it) {
-      const int64_t tile = blockIdx.x + it * gridDim.x;
-      const int64_t m = tile * kTile + row;
+    // stage the inputs of tile number `it` of this CTA: warps 0-3 encode the point, warps 4-7 stage feats + direction
+    auto stage_inputs = [&](int64_t it) {
+      const int64_t m = (blockIdx.x + it * gridDim.x) * kTile + row;
       const bool valid = m < p.M;
-      // ---- prologue: warps 0-3 encode the point, warps 4-7 stage feats and the direction ----
       if (hsel == 0) {
         float pe[C * 21 + 12];
 #pragma unroll
@@ -453,9 +460,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             pe_row<3, 4>(v, d);
           }
         }
-        store_row_chunks<32>(s_base, dir_chunk, row, d);
+        store_row_chunks<32>(s_base, dir_chunk + 4 * (int)(it & 1), row, d);
       }
       ptx::fence_proxy_async_smem();
+    };
+    if (my_tiles > 0) stage_inputs(0);
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t m = (blockIdx.x + it * gridDim.x) * kTile + row;
+      const bool valid = m < p.M;
+      // the tile's inputs were staged during the previous tile (or just above): tell the MMA warp
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -470,37 +483,40 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         epilogue_compute<3>(tmem_lane, part, hsel, b.acc_free + 8 * part, lane, pk);
         epilogue_store(tmem_lane + GATE_COL + part * 64 + hsel * 32, pk, b.a_ready + 8 * part, lane);
       }
-      // ---- L0..L7 ----
-      for (int l = 0; l < 8; ++l) epilogue_two_part<0>(tmem_lane, hsel, b, nfull, lane);
+      // ---- L0..L7; once L5 has retired (last reader of PE; feats died with GATE) the NEXT tile's inputs are
+      //      staged in the idle time of the remaining epilogues ----
+      for (int l = 0; l < 8; ++l) {
+        epilogue_two_part<0>(tmem_lane, hsel, b, nfull, lane);
+        if (l == 5 && it + 1 < my_tiles) stage_inputs(it + 1);
+      }
       // ---- FEAT + heads: the head accumulators (sigma + blend / scene flow / probs) are complete with
       //      FEAT part 0's commit; they are read into registers here, long before the next tile's
       //      GATE epilogue reuses the columns ----
       float head[12];
-      {
-        uint32_t p0[32];
-        wait_bar(b.acc_full, nfull[0]++ & 1, 320);
-        ptx::tc_fence_after();
-        if (hsel == 0) {
-          uint32_t r[16];
-          ptx::tmem_ld16(tmem_lane + HEAD_COL, r);
-          ptx::tc_wait_ld();
-          head[3] = __uint_as_float(r[0]);
-          if (p.kind == 1) {
-            head[4] = 1.f / (1.f + __expf(-__uint_as_float(r[1])));
-          } else if (p.kind == 2) {
+      wait_bar(b.acc_full, nfull[0]++ & 1, 320);
+      ptx::tc_fence_after();
+      if (hsel == 0) {
+        uint32_t r[16];
+        ptx::tmem_ld16(tmem_lane + HEAD_COL, r);
+        ptx::tc_wait_ld();
+        head[3] = __uint_as_float(r[0]);
+        if (p.kind == 1) {
+          head[4] = 1.f / (1.f + __expf(-__uint_as_float(r[1])));
+        } else if (p.kind == 2) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) head[4 + k] = tanhf(__uint_as_float(r[1 + k]));
+          for (int k = 0; k < 6; ++k) head[4 + k] = tanhf(__uint_as_float(r[1 + k]));
 #pragma unroll
-            for (int k = 0; k < 2; ++k) head[10 + k] = 1.f / (1.f + __expf(-__uint_as_float(r[7 + k])));
-          }
+          for (int k = 0; k < 2; ++k) head[10 + k] = 1.f / (1.f + __expf(-__uint_as_float(r[7 + k])));
         }
-        epilogue_compute<1>(tmem_lane, 0, hsel, b.acc_free, lane, p0);
+      }
+      {
+        uint32_t pk[32];
+        epilogue_compute<1>(tmem_lane, 0, hsel, b.acc_free, lane, pk);
+        epilogue_store(tmem_lane + ACT_COL + hsel * 32, pk, b.a_ready, lane);
         wait_bar(b.acc_full + 8, nfull[1]++ & 1, 321);
         ptx::tc_fence_after();
-        epilogue_store(tmem_lane + ACT_COL + hsel * 32, p0, b.a_ready, lane);
-        uint32_t p1[32];
-        epilogue_compute<1>(tmem_lane, 1, hsel, b.acc_free + 8, lane, p1);
-        epilogue_store(tmem_lane + ACT_COL + 64 + hsel * 32, p1, b.a_ready + 8, lane);
+        epilogue_compute<1>(tmem_lane, 1, hsel, b.acc_free + 8, lane, pk);
+        epilogue_store(tmem_lane + ACT_COL + 64 + hsel * 32, pk, b.a_ready + 8, lane);
       }
       // ---- VIEWS: relu -> v = activation columns [0, 128) ----
       {
@@ -645,8 +661,8 @@ int tc_pack(zest_net* net, cudaStream_t st) {
   ph->P = P; ph->Ppad = up(P, 32); ph->F = F; ph->Fpad = up(F, 16); ph->C = (P == 84) ? 4 : 3;
   ph->overlap = overlap ? 1 : 0;
   const int Ppad = ph->Ppad, Fpad = ph->Fpad;
-  // S = [PE | dirPE (4 chunks) | ones (2) | feats] + ring
-  ph->smem_bytes = (size_t)(Ppad / 8 + 6 + Fpad / 8) * kChunkBytes + (size_t)kStages * kStageBytes;
+  // S = [PE | dirPE x 2 (4 + 4 chunks) | ones (2) | feats] + ring
+  ph->smem_bytes = (size_t)(Ppad / 8 + 10 + Fpad / 8) * kChunkBytes + (size_t)kStages * kStageBytes;
 
   std::vector<TcStage> stages;
   std::vector<PackDesc> packs;
@@ -662,28 +678,24 @@ int tc_pack(zest_net* net, cudaStream_t st) {
   // revolution 0: GATE part 0, 1 (feats) | L0 part 0, 1 (PE)
   for (int part = 0; part < 2; ++part) stage(128, 128, net->w_gate, F, part * 128, 0, Fpad, F, net->b_gate);
   for (int part = 0; part < 2; ++part) stage(128, 128, net->w_pts[0], P, part * 128, 0, Ppad, P, net->b_pts[0]);
-  // L1..L7: per part two K halves; L5 = [pe | h4] gets the PE block first and an empty stage
-  for (int l = 1; l < 8; ++l)
-    for (int part = 0; part < 2; ++part) {
-      const int ld = (l == 5) ? P + W : W, c0 = (l == 5) ? P : 0;
-      if (l == 5) stage(128, 128, net->w_pts[l], ld, part * 128, 0, Ppad, P, -1);
-      stage(128, 128, net->w_pts[l], ld, part * 128, c0, 128, 128, -1);
-      stage(128, 128, net->w_pts[l], ld, part * 128, c0 + 128, 128, 128, net->b_pts[l]);
-      if (l == 5) skip();
-    }
-  // FEAT with the stacked small heads (N = 16) in front
+  // L1..L7: (p0, K lo) (p1, K lo) (p0, K hi + bias) (p1, K hi + bias); L5 = [pe | h4] starts with the PE blocks
+  for (int l = 1; l < 8; ++l) {
+    const int ld = (l == 5) ? P + W : W, c0 = (l == 5) ? P : 0;
+    if (l == 5) for (int part = 0; part < 2; ++part) stage(128, 128, net->w_pts[l], ld, part * 128, 0, Ppad, P, -1);
+    for (int part = 0; part < 2; ++part) stage(128, 128, net->w_pts[l], ld, part * 128, c0, 128, 128, -1);
+    for (int part = 0; part < 2; ++part) stage(128, 128, net->w_pts[l], ld, part * 128, c0 + 128, 128, 128, net->b_pts[l]);
+    if (l == 5) { skip(); skip(); }
+  }
+  // FEAT, with the stacked small heads (N = 16) behind the low-K stages
+  for (int part = 0; part < 2; ++part) stage(128, 128, net->w_feat, W, part * 128, 0, 128, 128, -1);
   stage(16, net->n_small, net->w_small, W, 0, 0, W, W, net->b_small);
-  stage(128, 128, net->w_feat, W, 0, 0, 128, 128, -1);
-  stage(128, 128, net->w_feat, W, 0, 128, 128, 128, net->b_feat);
-  skip();
-  stage(128, 128, net->w_feat, W, 128, 0, 128, 128, -1);
-  stage(128, 128, net->w_feat, W, 128, 128, 128, 128, net->b_feat);
-  skip(); skip();
-  // VIEWS: [feature | dirPE] (N = 128), RGB (N = 16) from v
+  for (int part = 0; part < 2; ++part) stage(128, 128, net->w_feat, W, part * 128, 128, 128, 128, net->b_feat);
+  // VIEWS: [feature | dirPE] (N = 128); RGB (N = 16) from v
   stage(128, 128, net->w_views, W + Cv, 0, 0, 128, 128, -1);
   stage(128, 128, net->w_views, W + Cv, 0, 128, 128, 128, -1);
   stage(128, 128, net->w_views, W + Cv, 0, W, 32, Cv, net->b_views);
   stage(16, 3, net->w_rgb, W / 2, 0, 0, W / 2, W / 2, net->b_rgb);
+  skip(); skip(); skip();
 
   ZEST_CHECK_ARG((int)stages.size() <= kMaxPlan && stages.size() % kStages == 0, "tc_pack: bad plan (%d stages)", (int)stages.size());
   for (auto& s : stages) ZEST_CHECK_ARG(s.bytes <= (uint32_t)kStageBytes && (s.bytes & 15u) == 0, "tc_pack: stage of %u bytes", s.bytes);
