@@ -159,10 +159,17 @@ int zest_composite_blend_bwd(const float* raw_dy, int ld_dy, const float* raw_ri
 /* ---- diagnostics -------------------------------------------------------------------------- */
 /* Runs D[128,N] = A[128,K] * B[N,K]^T through the tcgen05 path with the library's own smem
  * layouts (A, B bf16 row-major in global; D fp32 row-major).  Unit-test hook for the UMMA
- * descriptors; N multiple of 16 <= 256, K multiple of 16 <= 256.  variant 0 = the layout the
- * library uses; 1 = LBO/SBO swapped (diagnostic only, expected to fail). */
+ * descriptors; N multiple of 16 <= 256, K multiple of 16 <= 256.  variant 0 = A from shared
+ * memory (SS form); 1 = A as bf16 pairs in TMEM written with tcgen05.st (TS form, K % 32 == 0):
+ * the way the MLP kernel keeps its layer activations. */
 int zest_tc_selftest(const uint16_t* A, const uint16_t* B, float* D, int N, int K, int variant,
                      void* stream);
+/* Debug: device buffer of 1024 uint64 that builds with -DZEST_TC_TIMELINE fill with
+ * (tag << 48 | clock64) records of the MLP kernel's CTA 0 (no-op in normal builds). */
+int zest_tc_set_timeline(unsigned long long* buf);
+/* Characterisation probe: one CTA issues reps x 16 back-to-back UMMAs (M = 128, N, K = 16; ts = A from
+ * TMEM), optionally under TMEM-load traffic from its other warps.  out[0] = cycles to completion. */
+int zest_tc_rate_probe(int N, int reps, int ts, int ld_traffic, long long* out, void* stream);
 /* How many kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t zest_launch_count(void);
 

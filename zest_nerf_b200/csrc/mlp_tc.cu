@@ -71,7 +71,7 @@ struct PackDesc {  // how to build one weight block image from the fp32 blob
 struct TcPlanHost {
   std::vector<TcStage> stages;
   int n_stages = 0;
-  int P, Ppad, F, Fpad, C, overlap;
+  int P, Ppad, F, Fpad, C, overlap, gate_fp32;
   size_t smem_bytes;
 };
 
@@ -87,14 +87,22 @@ struct TcParams {
   int kind, out_ch, overlap;
   int64_t M; int64_t n_tiles;
   float* raw;
+  unsigned long long* tl;  // debug timeline buffer (ZEST_TC_TIMELINE builds only)
 };
+
+// ---- debug timeline (compiled in with -DZEST_TC_TIMELINE): (tag << 48 | clock) records of CTA 0, tile #3 ----
+#ifdef ZEST_TC_TIMELINE
+#define TL(seg, tag) do { if (tl_on) { p.tl[(seg) * 512 + tl_n[(seg) & 1]] = ((unsigned long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFull); tl_n[(seg) & 1]++; } } while (0)
+#else
+#define TL(seg, tag) do { } while (0)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, int tag) {
   if (ptx::mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!ptx::mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {  // a protocol bug must not hang the GPU (each try_wait suspends for a while)
+    if (++spins > (1u << 21)) {  // a protocol bug must not hang the GPU (each try_wait suspends for a while)
       printf("zest mlp_tc: barrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
       __trap();
     }
@@ -136,23 +144,25 @@ struct Bars {
 };
 
 // ---- epilogue of one accumulator part (bias already inside the accumulator) ----------------------
-// MODE 0: acc * gate, relu -> bf16 pairs        (L0..L7)
+// MODE 0: bf16(acc) * gate, relu -> bf16 pairs  (L0..L7; product and relu in one HFMA2.BF16.RELU)
+// MODE 4: acc * gate in fp32, relu -> bf16 pairs (L0..L7, ZEST_TC_GATE_FP32=1: one rounding less per activation)
 // MODE 1: acc -> bf16 pairs                      (FEAT)
 // MODE 2: acc, relu -> bf16 pairs                (VIEWS)
 // MODE 3: acc -> bf16 pairs                      (GATE; stored to the gate columns)
 // Loads the thread's 64 accumulator columns, releases the accumulator, returns 32 packed pairs.
 template <int MODE>
 __device__ __forceinline__ void epilogue_compute(uint32_t tmem_lane, int part, int hsel, uint32_t bar_free, int lane,
-                                                 uint32_t (&packed)[32]) {
+                                                 uint32_t (&packed)[32], long long* t_ld = nullptr) {
   uint32_t acc[2][32];
   ptx::tmem_ld32(tmem_lane + ACC_COL_OF(part) + hsel * 64, acc[0]);
   ptx::tmem_ld32(tmem_lane + ACC_COL_OF(part) + hsel * 64 + 32, acc[1]);
   uint32_t g[2][16];
-  if (MODE == 0) {
+  if (MODE == 0 || MODE == 4) {
     ptx::tmem_ld16(tmem_lane + GATE_COL + part * 64 + hsel * 32, g[0]);
     ptx::tmem_ld16(tmem_lane + GATE_COL + part * 64 + hsel * 32 + 16, g[1]);
   }
   ptx::tc_wait_ld();
+  if (t_ld) *t_ld = clock64();
   // the accumulator half is drained: the MMA warp may overwrite it
   ptx::tc_fence_before();
   __syncwarp();
@@ -162,12 +172,13 @@ __device__ __forceinline__ void epilogue_compute(uint32_t tmem_lane, int part, i
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
       float v0 = __uint_as_float(acc[h][j]), v1 = __uint_as_float(acc[h][j + 1]);
-      if (MODE == 0) {
+      if (MODE == 4) {
         const uint32_t g01 = g[h][j / 2];
         ptx::mul_f32x2(v0, v1, ptx::bf16_lo(g01), ptx::bf16_hi(g01));
       }
       uint32_t pk = ptx::pack_bf16(v0, v1);
-      if (MODE == 0 || MODE == 2) pk = ptx::relu_bf16x2(pk);
+      if (MODE == 0) pk = ptx::mul_relu_bf16x2(pk, g[h][j / 2]);
+      if (MODE == 4 || MODE == 2) pk = ptx::relu_bf16x2(pk);
       packed[h * 16 + j / 2] = pk;
     }
   }
@@ -257,7 +268,7 @@ __device__ __forceinline__ void mma_skip(MmaCtx& c) {
   ++c.n_issued;
 }
 
-template <int C>  // C = 3 (static: xyz) or 4 (dynamic: xyz + t)
+template <int C, bool GATE32>  // C = 3 (static: xyz) or 4 (dynamic: xyz + t); GATE32: fp32 gate multiply
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_bars[2 * kStages + 6];
@@ -328,6 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     // order, and before the next one can happen; every op below therefore waits on all four barriers
     // at least once before its last commit.  The schedule is straight-line code that must walk the
     // ring stages in exactly the order tc_pack() laid them out (checked per tile against n_stages).
+    int tl_n[2] = {0, 0}; (void)tl_n;
     MmaCtx c{b, 0u, 1u, 0u, (((s_base + ones_chunk * kChunkBytes) >> 4) & 0x3FFF) | kALbo, (ring >> 4) & 0x3FFF};
     const uint32_t pe_lo = ((s_base >> 4) & 0x3FFF) | kALbo;
     const uint32_t dir_lo[2] = {pe_lo + dir_chunk * (kChunkBytes >> 4), pe_lo + (dir_chunk + 4) * (kChunkBytes >> 4)};
@@ -343,9 +355,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       mma_stage<128, false, 1>(c, feat_lo, nk_f, acc1, true, true, 1);
       c.next_op();
       if (!ov) c.wait(15u);
-      c.wait(4u);
+      c.wait(4u | 1u);   // every barrier of part X must be observed before the commit that lets X complete again
       mma_stage<128, false, 2>(c, pe_lo, nk_p, acc0, true, true, 0);
-      c.wait(8u | 3u);
+      c.wait(8u | 2u);
       mma_stage<128, false, 3>(c, pe_lo, nk_p, acc1, true, true, 1);
       c.end_revolution();
       // ---- L1..L7: (p0, K lo) (p1, K lo) (p0, K hi) (p1, K hi); L5 = [pe | h4] starts with the PE blocks (smem) ----
@@ -368,13 +380,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
           mma_skip<3>(c);
           c.end_revolution();
         } else {
+#ifdef ZEST_TC_TIMELINE
+          const bool tl_on = p.tl && blockIdx.x == 0 && it == 3 && lane == 0;
+#endif
           c.wait(4u | 1u);
+          TL(1, 100 * l + 50);
           mma_stage<128, true, 0>(c, act, 8, acc0, true, false, -1);
+          TL(1, 100 * l + 51);
           c.wait(8u);
+          TL(1, 100 * l + 52);
           mma_stage<128, true, 1>(c, act, 8, acc1, true, false, -1);
+          TL(1, 100 * l + 53);
           c.wait(2u);
+          TL(1, 100 * l + 54);
           mma_stage<128, true, 2>(c, act + 64, 8, acc0, false, true, 0);
+          TL(1, 100 * l + 55);
           mma_stage<128, true, 3>(c, act + 64, 8, acc1, false, true, 1);
+          TL(1, 100 * l + 56);
           c.end_revolution();
         }
       }
@@ -415,6 +437,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     const int q = warp & 3, hsel = warp >> 2;
     const int row = q * 32 + lane;
     uint32_t nfull[2] = {0, 0};
+    int tl_n[2] = {0, 0}; (void)tl_n;
     const uint32_t tmem_lane = tmem + ((uint32_t)(q * 32) << 16);
     // stage the inputs of tile number `it` of this CTA: warps 0-3 encode the point, warps 4-7 stage feats + direction
     auto stage_inputs = [&](int64_t it) {
@@ -486,7 +509,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       // ---- L0..L7; once L5 has retired (last reader of PE; feats died with GATE) the NEXT tile's inputs are
       //      staged in the idle time of the remaining epilogues ----
       for (int l = 0; l < 8; ++l) {
-        epilogue_two_part<0>(tmem_lane, hsel, b, nfull, lane);
+#ifdef ZEST_TC_TIMELINE
+        const bool tl_on = p.tl && blockIdx.x == 0 && it == 3 && warp == 0 && lane == 0;
+        for (int part = 0; part < 2; ++part) {
+          uint32_t pk[32];
+          long long t_ld = 0;
+          wait_bar(b.acc_full + 8 * part, nfull[part]++ & 1, 310 + part);
+          ptx::tc_fence_after();
+          TL(0, 100 * l + 10 * part + 0);
+          epilogue_compute<GATE32 ? 4 : 0>(tmem_lane, part, hsel, b.acc_free + 8 * part, lane, pk, &t_ld);
+          if (tl_on) { p.tl[tl_n[0]] = ((unsigned long long)(100 * l + 10 * part + 1) << 48) | (t_ld & 0xFFFFFFFFFFFFull); tl_n[0]++; }
+          TL(0, 100 * l + 10 * part + 2);
+          epilogue_store(tmem_lane + ACT_COL + part * 64 + hsel * 32, pk, b.a_ready + 8 * part, lane);
+          TL(0, 100 * l + 10 * part + 3);
+        }
+#else
+        epilogue_two_part<GATE32 ? 4 : 0>(tmem_lane, hsel, b, nfull, lane);
+#endif
         if (l == 5 && it + 1 < my_tiles) stage_inputs(it + 1);
       }
       // ---- FEAT + heads: the head accumulators (sigma + blend / scene flow / probs) are complete with
@@ -637,6 +676,63 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const uint16_t* __r
   if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 512); }
 }
 
+// ---- tensor-pipe rate probe: `reps` x 16 back-to-back UMMAs (M = 128, N, K = 16), optionally with the
+// other three warps hammering TMEM loads, as the epilogue warps do.  out[0] = cycles from first issue to commit.
+template <int N>
+__global__ void __launch_bounds__(128, 1) tc_rate_kernel(int reps, int ts, int ld_traffic, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t s_tmem;
+  __shared__ volatile int s_stop;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (128 + 256) * 256 * 2 / 16; i += 128) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) { ptx::mbar_init(ptx::smem_u32(&bar), 1); ptx::fence_mbar_init(); s_stop = 0; }
+  if (warp == 0) { ptx::tmem_alloc(ptx::smem_u32(&s_tmem), 512); ptx::tmem_relinquish(); }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t a_s = ptx::smem_u32(smem_raw), b_s = a_s + 128 * 256 * 2;
+  if (warp == 0) {
+    // warp-convergent issue with warp-uniform operands, like the MLP kernel's MMA warp
+    constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t a_lo = ((a_s >> 4) & 0x3FFF) | kALbo, b_lo = ((b_s >> 4) & 0x3FFF) | ((uint32_t)N << 16);
+    const uint32_t act = tmem + ACT_COL;
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          if (ts) ptx::mma_bf16_ts(tmem, act + 8 * k, kHi | (b_lo + 2u * N * k), kIdesc, 1u);
+          else ptx::mma_bf16_ss(tmem, kHi | (a_lo + ((2u * kChunkBytes) >> 4) * k), kHi | (b_lo + 2u * N * k), kIdesc, 1u);
+        }
+      }
+      __syncwarp();
+    }
+    if (ptx::elect_one()) ptx::mma_commit(ptx::smem_u32(&bar));
+    __syncwarp();
+    const long long t1 = clock64();
+    while (!ptx::mbar_try_wait(ptx::smem_u32(&bar), 0)) { }
+    const long long t2 = clock64();
+    if (tid == 0) { out[0] = t2 - t0; out[1] = t1 - t0; s_stop = 1; }
+  } else if (ld_traffic) {
+    // TMEM read traffic on the gate columns (not touched by the MMAs) from the other three lane quarters
+    uint32_t r[32];
+    long long n = 0;
+    while (!s_stop) {
+      ptx::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + GATE_COL, r);
+      ptx::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + GATE_COL + 32, r);
+      ptx::tc_wait_ld();
+      ++n;
+    }
+    if ((tid & 31) == 0) out[2 + warp] = n * 2 + (r[0] & 1);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 512); }
+}
+
 // ------------------------------------------------------------------------------------------------
 static inline int up(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -660,6 +756,7 @@ int tc_pack(zest_net* net, cudaStream_t st) {
   const int W = 256, P = net->in_pts, F = net->in_feat, Cv = net->in_views;
   ph->P = P; ph->Ppad = up(P, 32); ph->F = F; ph->Fpad = up(F, 16); ph->C = (P == 84) ? 4 : 3;
   ph->overlap = overlap ? 1 : 0;
+  ph->gate_fp32 = (getenv("ZEST_TC_GATE_FP32") && atoi(getenv("ZEST_TC_GATE_FP32")) != 0) ? 1 : 0;
   const int Ppad = ph->Ppad, Fpad = ph->Fpad;
   // S = [PE | dirPE x 2 (4 + 4 chunks) | ones (2) | feats] + ring
   ph->smem_bytes = (size_t)(Ppad / 8 + 10 + Fpad / 8) * kChunkBytes + (size_t)kStages * kStageBytes;
@@ -716,7 +813,10 @@ int tc_pack(zest_net* net, cudaStream_t st) {
   return ZEST_OK;
 }
 
+static unsigned long long* g_timeline = nullptr;
+
 static int tc_launch(const zest_net* net, TcParams& p, cudaStream_t st) {
+  p.tl = g_timeline;
   if (!net->packed) { set_error("zest_mlp_fwd_tc: net not packed"); return ZEST_E_STATE; }
   if (!tc_supported(net) || !net->tc_plan_host) {
     set_error("zest_mlp_fwd_tc: the tensor-core path supports width=256 depth=8 skip=4 in_pts in {63,84} in_feat<=64 in_views=27 "
@@ -731,13 +831,14 @@ static int tc_launch(const zest_net* net, TcParams& p, cudaStream_t st) {
   p.n_tiles = (p.M + kTile - 1) / kTile;
   if (p.M == 0) return ZEST_OK;
   const int grid = (int)(p.n_tiles < num_sms() ? p.n_tiles : num_sms());
-  if (ph->C == 3) {
-    ZEST_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ph->smem_bytes));
-    mlp_tc_kernel<3><<<grid, kThreads, ph->smem_bytes, st>>>(p);
-  } else {
-    ZEST_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ph->smem_bytes));
-    mlp_tc_kernel<4><<<grid, kThreads, ph->smem_bytes, st>>>(p);
-  }
+#define ZEST_TC_GO(CC, G32)                                                                                              \
+  do {                                                                                                                   \
+    ZEST_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<CC, G32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ph->smem_bytes)); \
+    mlp_tc_kernel<CC, G32><<<grid, kThreads, ph->smem_bytes, st>>>(p);                                                  \
+  } while (0)
+  if (ph->C == 3) { if (ph->gate_fp32) ZEST_TC_GO(3, true); else ZEST_TC_GO(3, false); }
+  else { if (ph->gate_fp32) ZEST_TC_GO(4, true); else ZEST_TC_GO(4, false); }
+#undef ZEST_TC_GO
   ZEST_LAUNCH_CHECK();
   return ZEST_OK;
 }
@@ -764,6 +865,27 @@ extern "C" int zest_mlp_fwd_tc_x(const zest_net* net, const float* x, int ldx, i
   p.x = x; p.ldx = ldx; p.M = M; p.raw = raw; p.S = 1;
   return tc_launch(net, p, (cudaStream_t)stream);
 }
+
+// debug / characterisation: out[0] = cycles for reps x 16 UMMAs (M = 128, N, K = 16), out[1] = issue cycles
+extern "C" int zest_tc_rate_probe(int N, int reps, int ts, int ld_traffic, long long* out, void* stream) {
+  ZEST_CHECK_ARG(out && N >= 16 && N <= 256 && (N % 16) == 0 && reps > 0, "zest_tc_rate_probe: bad arguments");
+  const size_t smem = (size_t)(128 + 256) * 256 * 2;
+#define ZEST_RATE(NN)                                                                                              \
+  case NN:                                                                                                         \
+    ZEST_CUDA(cudaFuncSetAttribute(tc_rate_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    tc_rate_kernel<NN><<<1, 128, smem, (cudaStream_t)stream>>>(reps, ts, ld_traffic, out);                       \
+    break;
+  switch (N) {
+    ZEST_RATE(16) ZEST_RATE(64) ZEST_RATE(128) ZEST_RATE(256)
+    default: set_error("zest_tc_rate_probe: N must be 16, 64, 128 or 256"); return ZEST_E_ARG;
+  }
+#undef ZEST_RATE
+  ZEST_LAUNCH_CHECK();
+  return ZEST_OK;
+}
+
+// debug: device buffer of 1024 u64 that ZEST_TC_TIMELINE builds fill with (tag << 48 | clock) records
+extern "C" int zest_tc_set_timeline(unsigned long long* buf) { g_timeline = buf; return ZEST_OK; }
 
 extern "C" int zest_tc_selftest(const uint16_t* A, const uint16_t* B, float* D, int N, int K, int variant, void* stream) {
   ZEST_CHECK_ARG(A && B && D && N >= 16 && N <= 256 && (N % 16) == 0 && K >= 16 && K <= 256 && (K % 16) == 0,

@@ -190,6 +190,13 @@ __device__ __forceinline__ uint32_t relu_bf16x2(uint32_t p) {
   return r;
 }
 
+// relu(a * b) on packed bf16 pairs, one rounding (HFMA2.BF16_V2.RELU)
+__device__ __forceinline__ uint32_t mul_relu_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(0u));
+  return r;
+}
+
 __device__ __forceinline__ uint4 ld_smem_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
