@@ -164,7 +164,7 @@ int zest_composite_blend_bwd(const float* raw_dy, int ld_dy, const float* raw_ri
  * the way the MLP kernel keeps its layer activations. */
 int zest_tc_selftest(const uint16_t* A, const uint16_t* B, float* D, int N, int K, int variant,
                      void* stream);
-/* Debug: device buffer of 1024 uint64 that builds with -DZEST_TC_TIMELINE fill with
+/* Debug: device buffer of 4096 uint64 that builds with -DZEST_TC_TIMELINE fill with
  * (tag << 48 | clock64) records of the MLP kernel's CTA 0 (no-op in normal builds). */
 int zest_tc_set_timeline(unsigned long long* buf);
 /* Characterisation probe: one CTA issues reps x 16 back-to-back UMMAs (M = 128, N, K = 16; ts = A from

@@ -15,7 +15,7 @@ net = sc.net_static
 M = 148 * 128 * 8
 g = torch.Generator().manual_seed(0)
 x = torch.randn((M, 63 + 20 + 27), generator=g).cuda()
-buf = torch.zeros(1024, dtype=torch.int64, device="cuda")
+buf = torch.zeros(4096, dtype=torch.int64, device="cuda")
 lib.zest_tc_set_timeline(C.c_void_p(buf.data_ptr()))
 with torch.no_grad(), ops.mlp_mode("bf16"):
     for _ in range(3):
@@ -25,8 +25,8 @@ torch.cuda.synchronize()
 lib.zest_tc_set_timeline(None)
 v = buf.cpu().numpy()
 ev = []
-for seg, name in ((0, "epi"), (1, "mma")):
-    for w in v[seg * 512:(seg + 1) * 512]:
+for seg, name in [(w, f"epi{w}") for w in range(8)] + [(9, "mma")]:
+    for w in v[seg * 256:(seg + 1) * 256]:
         w = int(w) & 0xFFFFFFFFFFFFFFFF
         if w:
             ev.append((w & 0xFFFFFFFFFFFF, name, w >> 48))
@@ -37,10 +37,11 @@ MMA = {50: "wait(free0|rdy0) ok", 51: "p0.lo issued", 52: "wait(free1) ok", 53: 
 prev = t0
 for t, name, tag in ev:
     l, r = divmod(tag, 100)
-    if name == "epi":
+    if name.startswith("epi"):
         part, k = divmod(r, 10)
         desc = f"L{l} part{part} {EPI.get(k, k)}"
     else:
         desc = f"L{l} {MMA.get(r, r)}"
-    print(f"{t - t0:8d} (+{t - prev:5d})  {name}  {desc}")
-    prev = t
+    if "-v" in sys.argv or name in ("mma", "epi0") or desc.endswith("arrived"):
+        print(f"{t - t0:8d} (+{t - prev:5d})  {name:5s} {desc}")
+        prev = t
