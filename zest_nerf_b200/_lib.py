@@ -58,8 +58,11 @@ def load():
             raise RuntimeError(
                 f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a).  zest_nerf_b200 has no CPU / PyTorch fallback.")
-        lib = C.CDLL(LIB_PATH)
+        path = os.environ.get("ZEST_B200_LIB", LIB_PATH)   # developer A/B of kernel variants; same ABI
+        lib = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
+            if path != LIB_PATH and not hasattr(lib, name):
+                continue   # an older variant without the newest debug hooks
             fn = getattr(lib, name)  # AttributeError if the .so is stale
             fn.restype, fn.argtypes = res, args
         _lib = lib

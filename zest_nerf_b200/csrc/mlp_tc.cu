@@ -84,7 +84,7 @@ struct TcParams {
   const float* dirs; int S;
   const float* x; int ldx;
   int P, Ppad, F, Fpad;
-  int kind, out_ch, overlap, spin, probe;
+  int kind, out_ch, overlap;
   int64_t M; int64_t n_tiles;
   float* raw;
   unsigned long long* tl;  // debug timeline buffer (ZEST_TC_TIMELINE builds only)
@@ -103,18 +103,6 @@ __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, int tag)
   uint32_t spins = 0;
   while (!ptx::mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 21)) {  // a protocol bug must not hang the GPU (each try_wait suspends for a while)
-      printf("zest mlp_tc: barrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
-      __trap();
-    }
-  }
-}
-
-// latency-critical variant: spin on the non-blocking test_wait (try_wait's hardware suspend was measured to
-// add a few hundred cycles between the completing arrival and the waiter's wake-up)
-__device__ __forceinline__ void spin_bar(uint32_t bar, uint32_t parity, int tag) {
-  uint32_t spins = 0;
-  while (!ptx::mbar_test_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
       printf("zest mlp_tc: barrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
       __trap();
     }
@@ -234,42 +222,12 @@ struct MmaCtx {
   uint32_t ones_lo, ring_lo;
   __device__ __forceinline__ void next_op() { par ^= 1u; }
   __device__ __forceinline__ void wait(uint32_t need) {
-    if (spin) {
-      if (need & 1u) spin_bar(b.a_ready, par, 200);
-      if (need & 2u) spin_bar(b.a_ready + 8, par, 201);
-      if (need & 4u) spin_bar(b.acc_free, par, 202);
-      if (need & 8u) spin_bar(b.acc_free + 8, par, 203);
-    } else {
-      if (need & 1u) wait_bar(b.a_ready, par, 200);
-      if (need & 2u) wait_bar(b.a_ready + 8, par, 201);
-      if (need & 4u) wait_bar(b.acc_free, par, 202);
-      if (need & 8u) wait_bar(b.acc_free + 8, par, 203);
-    }
+    if (need & 1u) wait_bar(b.a_ready, par, 200);
+    if (need & 2u) wait_bar(b.a_ready + 8, par, 201);
+    if (need & 4u) wait_bar(b.acc_free, par, 202);
+    if (need & 8u) wait_bar(b.acc_free + 8, par, 203);
   }
-  // non-blocking probe of the same barriers (issue early, consume with ensure(): a barrier check costs ~100
-  // cycles of latency even when it is satisfied, so checks that are usually satisfied are taken off the
-  // issue path by probing them before the previous block of MMAs is issued)
-  __device__ __forceinline__ uint32_t probe(uint32_t need) {
-    uint32_t ok = 0;
-    if (!use_probe) return 0u;
-    if (need & 1u) ok |= ptx::mbar_test_wait(b.a_ready, par) ? 1u : 0u;
-    if (need & 2u) ok |= ptx::mbar_test_wait(b.a_ready + 8, par) ? 2u : 0u;
-    if (need & 4u) ok |= ptx::mbar_test_wait(b.acc_free, par) ? 4u : 0u;
-    if (need & 8u) ok |= ptx::mbar_test_wait(b.acc_free + 8, par) ? 8u : 0u;
-    return ok;
-  }
-  __device__ __forceinline__ void ensure(uint32_t need, uint32_t probed) { if (need & ~probed) wait(need & ~probed); }
   __device__ __forceinline__ void end_revolution() { phase ^= 1u; }
-  uint32_t spin;     // poll with test_wait instead of blocking in try_wait
-  uint32_t use_probe;
-  uint32_t pre_ok;   // result of the early probe of the next ring slot's full barrier
-  // the weights of ring slot SLOT have landed; start probing the next slot (slots are always walked 0,1,2,3)
-  template <int SLOT>
-  __device__ __forceinline__ void acquire() {
-    if (!pre_ok) wait_bar(b.full + 8 * SLOT, phase, 220 + SLOT);
-    ptx::tc_fence_after();
-    pre_ok = (use_probe && ptx::mbar_test_wait(b.full + 8 * ((SLOT + 1) % kStages), SLOT == kStages - 1 ? phase ^ 1u : phase)) ? 1u : 0u;
-  }
 };
 
 // One ring stage at compile-time SLOT: n_k16 K = 16 steps of N weight rows.
@@ -279,7 +237,8 @@ struct MmaCtx {
 template <int N, bool TS, int SLOT>
 __device__ __forceinline__ void mma_stage(MmaCtx& c, uint32_t a, int n_k16, uint32_t d_tmem, bool first, bool bias, int commit_part) {
   constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-  c.template acquire<SLOT>();
+  wait_bar(c.b.full + 8 * SLOT, c.phase, 220 + SLOT);
+  ptx::tc_fence_after();
   // B descriptor low word; one K = 16 step advances B by 2 chunks of N rows x 16 B
   uint32_t b_lo = (c.ring_lo + SLOT * (kStageBytes >> 4)) | ((uint32_t)N << 16);
   if (ptx::elect_one()) {
@@ -303,7 +262,7 @@ __device__ __forceinline__ void mma_stage(MmaCtx& c, uint32_t a, int n_k16, uint
 // an empty stage: hand the slot straight back to the producer
 template <int SLOT>
 __device__ __forceinline__ void mma_skip(MmaCtx& c) {
-  c.template acquire<SLOT>();
+  wait_bar(c.b.full + 8 * SLOT, c.phase, 230 + SLOT);
   if (ptx::elect_one()) ptx::mbar_arrive(c.b.empty + 8 * SLOT);
   __syncwarp();
   ++c.n_issued;
@@ -381,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     // at least once before its last commit.  The schedule is straight-line code that must walk the
     // ring stages in exactly the order tc_pack() laid them out (checked per tile against n_stages).
     int tl_n[2] = {0, 0}; (void)tl_n;
-    MmaCtx c{b, 0u, 1u, 0u, (((s_base + ones_chunk * kChunkBytes) >> 4) & 0x3FFF) | kALbo, (ring >> 4) & 0x3FFF, (uint32_t)p.spin, (uint32_t)p.probe, 0u};
+    MmaCtx c{b, 0u, 1u, 0u, (((s_base + ones_chunk * kChunkBytes) >> 4) & 0x3FFF) | kALbo, (ring >> 4) & 0x3FFF};
     const uint32_t pe_lo = ((s_base >> 4) & 0x3FFF) | kALbo;
     const uint32_t dir_lo[2] = {pe_lo + dir_chunk * (kChunkBytes >> 4), pe_lo + (dir_chunk + 4) * (kChunkBytes >> 4)};
     const uint32_t feat_lo = pe_lo + feat_chunk * (kChunkBytes >> 4);
@@ -424,19 +383,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
 #ifdef ZEST_TC_TIMELINE
           const bool tl_on = p.tl && blockIdx.x == 0 && it == 3 && lane == 0;
 #endif
-          // a_ready[0] implies acc_free[0] (every warp arrives on acc_free[0] before a_ready[0]), so only the
-          // former is waited on; acc_free[1] / a_ready[1] are normally long satisfied when needed: probed early
-          c.wait(1u);
+          c.wait(4u | 1u);
           TL(9, 100 * l + 50);
-          uint32_t pr = c.probe(8u);
           mma_stage<128, true, 0>(c, act, 8, acc0, true, false, -1);
           TL(9, 100 * l + 51);
-          c.ensure(8u, pr);
-          pr = c.probe(2u);
+          c.wait(8u);
           TL(9, 100 * l + 52);
           mma_stage<128, true, 1>(c, act, 8, acc1, true, false, -1);
           TL(9, 100 * l + 53);
-          c.ensure(2u, pr);
+          c.wait(2u);
           TL(9, 100 * l + 54);
           mma_stage<128, true, 2>(c, act + 64, 8, acc0, false, true, 0);
           TL(9, 100 * l + 55);
@@ -873,8 +828,6 @@ static int tc_launch(const zest_net* net, TcParams& p, cudaStream_t st) {
   memcpy(p.plan, ph->stages.data(), ph->stages.size() * sizeof(TcStage)); p.n_stages = ph->n_stages; p.blob = (const uint8_t*)net->tc_blob;
   p.P = ph->P; p.Ppad = ph->Ppad; p.F = ph->F; p.Fpad = ph->Fpad;
   p.kind = net->kind; p.out_ch = net->out_ch; p.overlap = ph->overlap;
-  p.probe = !(getenv("ZEST_TC_PROBE") && atoi(getenv("ZEST_TC_PROBE")) == 0) ? 1 : 0;
-  p.spin = (getenv("ZEST_TC_SPIN") && atoi(getenv("ZEST_TC_SPIN")) != 0) ? 1 : 0;
   p.n_tiles = (p.M + kTile - 1) / kTile;
   if (p.M == 0) return ZEST_OK;
   const int grid = (int)(p.n_tiles < num_sms() ? p.n_tiles : num_sms());
