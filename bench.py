@@ -252,7 +252,7 @@ def main():
     achieved = flops / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
     peak = pk["bf16_tflops_sustained"]
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "mlp_tc_kernel (2 launches/step: static + dynamic net)",
+                "traffic": None, "kernel": "mlp_tc_kernel (2 launches/step: static + dynamic net; the feature gather runs inside it)",
                 "peak_source": f"bf16_tflops_sustained, {src}", "mlp_ms_per_step": mlp_ms,
                 "whole_step_frac": flops / (total_ms / args.steps * 1e-3) / 1e12 / peak,
                 "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()}}

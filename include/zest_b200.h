@@ -121,6 +121,18 @@ int zest_mlp_bwd_f32(const zest_net* net, const float* x, int ldx, int64_t M, co
 int zest_mlp_fwd_tc(const zest_net* net, const float* ndc, int ndc_ld, int has_t, float t,
                     const float* feats, int ldf, const float* dirs, int S, int64_t M, float* raw,
                     void* stream);
+/* The fused hot path: the same kernel with the feature gather inside.  Replaces gen_pts_feats
+ * (renderer.py:51-72: index_point_feature + build_color_volume) + prepare_pts (renderer.py:246-297:
+ * Embedding + cat) + run_network (renderer.py:237-242 -> networks.py:150-221) in one launch: loader
+ * warps sample the channels-last volume [D,Hv,Wv,8] and the views [V,H,W,4] for the NEXT 128-sample
+ * tile (same arithmetic as zest_gather_fwd, bit-identical indices) while the current tile is in the
+ * tensor pipe.  feats_out (optional, may be NULL) receives the gathered features in fp32
+ * ([M, ldfo]: the reference's `input_feat`).  Needs net.in_feat == 8 + 4 V, V <= 14. */
+int zest_gather_mlp_fwd_tc(const zest_net* net, const float* rays_pts, const float* rays_ndc,
+                           int ndc_ld, int has_t, float t, const float* vol_cl, int D, int Hv, int Wv,
+                           const float* img_cl, int V, int H, int W, const float* cams,
+                           const float* dirs, int S, int64_t M, float* feats_out, int ldfo,
+                           float* raw, void* stream);
 /* same kernel fed with an already assembled x (module boundary MVSNeRF.forward(x)). */
 int zest_mlp_fwd_tc_x(const zest_net* net, const float* x, int ldx, int64_t M, float* raw,
                       void* stream);

@@ -200,6 +200,31 @@ def test_mlp_tensor_core_multi_tile_persistent_loop(zops):
         assert rel <= 2e-2, rel
 
 
+@pytest.mark.parametrize("name", ["dynamic_val", "dynamic_val_v10"])
+def test_fused_gather_mlp_is_bit_identical_to_the_two_kernel_path(zops, name):
+    """zest_gather_mlp_fwd_tc (loader warps gather inside the MLP kernel) == zest_gather_fwd + zest_mlp_fwd_tc,
+    bit for bit: same index arithmetic, same fp32 features, same bf16 operands."""
+    sc, rays, mode, _ = build_case(name)
+    d = to_dev(sc, rays)
+    R, S = d["rays_pts"].shape[1:3]
+    pts = d["rays_pts"].reshape(-1, 3).contiguous()
+    ndc = d["rays_ndc"].reshape(-1, 3).contiguous()
+    for net, vol, imgs, cam, t in ((sc.net_static, sc.vol_static, sc.imgs[:, :-1].contiguous(), sc.im_cam_mat, None),
+                                   (sc.net_dynamic, sc.vol_dynamic, sc.nb_imgs, sc.nb_cam_mat, 0.1)):
+        V = imgs.shape[1]
+        vol_cl, img_cl, cams = zops.pack_volume(vol), zops.pack_images(imgs), zops.cam_table(cam, V)
+        _, dirs = zops.dirfeat(d["rays_dir"], cams)
+        pk, _ = zops.packed(net)
+        feats = zops.gather_fwd(pts, ndc, vol_cl, img_cl, cams, R, S, 8 + 4 * V)
+        raw2 = zops.mlp_tc(pk, ndc, t, feats, dirs, S)
+        raw1, feats1 = zops.gather_mlp_tc(pk, pts, ndc, t, vol_cl, img_cl, cams, dirs, R, S, want_feats=True)
+        torch.cuda.synchronize()
+        assert torch.equal(feats1, feats)
+        assert torch.equal(raw1, raw2)
+        raw3, none = zops.gather_mlp_tc(pk, pts, ndc, t, vol_cl, img_cl, cams, dirs, R, S)
+        assert none is None and torch.equal(raw3, raw2)
+
+
 # ----------------------------------------------------------------------------- composite
 def test_composite_kernels_match_oracle(zops):
     g = torch.Generator().manual_seed(2)

@@ -1,9 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
 echo "== tc ==" > gpurun_out/run2.log
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "selftest or tensor_core or bf16 or sharding" >> gpurun_out/run2.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "selftest or tensor_core or bf16 or sharding or fused" >> gpurun_out/run2.log 2>&1
 echo "== rest ==" >> gpurun_out/run2.log
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "not (selftest or tensor_core or bf16 or sharding)" >> gpurun_out/run2.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "not (selftest or tensor_core or bf16 or sharding or fused)" >> gpurun_out/run2.log 2>&1
 echo "== smoke ==" >> gpurun_out/run2.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" >> gpurun_out/run2.log 2>&1
 echo "== bench bf16 cfg2 serial ==" >> gpurun_out/run2.log

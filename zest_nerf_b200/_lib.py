@@ -38,6 +38,7 @@ SIGNATURES = {
     "zest_mlp_bwd_f32": (_i, [_p, _p, _i, _l, _p, _p, _p, C.POINTER(_p), _i, _p]),
     "zest_mlp_fwd_tc": (_i, [_p, _p, _i, _i, _f, _p, _i, _p, _i, _l, _p, _p]),
     "zest_mlp_fwd_tc_x": (_i, [_p, _p, _i, _l, _p, _p]),
+    "zest_gather_mlp_fwd_tc": (_i, [_p, _p, _p, _i, _i, _f, _p, _i, _i, _i, _p, _i, _i, _i, _p, _p, _i, _l, _p, _i, _p, _p]),
     "zest_composite_static_fwd": (_i, [_p, _i, _p, _p, _p, _l, _i, _i, _f, _p, _p, _p, _p, _p, _p]),
     "zest_composite_static_bwd": (_i, [_p, _i, _p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
     "zest_composite_blend_fwd": (_i, [_p, _i, _p, _i, _p, _p, _p, _l, _i, _f, _p, _p, _p, _p, _p, _p, _p]),

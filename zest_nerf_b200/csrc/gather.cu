@@ -11,7 +11,7 @@
 // corner).  Thread mapping: lane -> ray, warp -> sample slot, so the 32 lanes of a warp touch 32
 // horizontally adjacent target pixels at the same depth index: their voxels / source pixels are
 // neighbours in memory (4 target pixels per voxel in x) and share cache lines in L1/L2.
-#include "common.cuh"
+#include "gather_core.cuh"
 
 namespace zest {
 
@@ -82,50 +82,8 @@ __global__ void __launch_bounds__(32 * kGatherWarps) gather_fwd_kernel(GatherPar
 
   if (HAS_VOL) {
     const float* n = p.ndc + m * p.ndc_ld;
-    const float nx = __ldg(n), ny = __ldg(n + 1), nz = __ldg(n + 2);
-    // utils.py:451  grid = ndc * 2 - 1.0 ; then ATen unnormalize (align_corners) per axis
-    const float ix = safe_int_range(unnormalize(__fsub_rn(__fmul_rn(nx, 2.f), 1.f), p.Wv));
-    const float iy = safe_int_range(unnormalize(__fsub_rn(__fmul_rn(ny, 2.f), 1.f), p.Hv));
-    const float iz = safe_int_range(unnormalize(__fsub_rn(__fmul_rn(nz, 2.f), 1.f), p.D));
-    const float fx0 = floorf(ix), fy0 = floorf(iy), fz0 = floorf(iz);
-    const int x0 = (int)fx0, y0 = (int)fy0, z0 = (int)fz0;
-    if (p.vox_idx) {
-      p.vox_idx[m * 3 + 0] = x0;
-      p.vox_idx[m * 3 + 1] = y0;
-      p.vox_idx[m * 3 + 2] = z0;
-    }
-    const float wx[2] = {(fx0 + 1.f) - ix, ix - fx0};
-    const float wy[2] = {(fy0 + 1.f) - iy, iy - fy0};
-    const float wz[2] = {(fz0 + 1.f) - iz, iz - fz0};
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    // issue all in-bounds corner loads first (16 independent LDG.128), then blend
-    float4 c[8][2];
-    float w[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
-      const int x = x0 + dx, y = y0 + dy, z = z0 + dz;
-      const bool ok = (unsigned)x < (unsigned)p.Wv && (unsigned)y < (unsigned)p.Hv && (unsigned)z < (unsigned)p.D;
-      w[k] = ok ? wx[dx] * wy[dy] * wz[dz] : 0.f;
-      if (ok) {
-        const float4* q = reinterpret_cast<const float4*>(p.vol + (((int64_t)z * p.Hv + y) * p.Wv + x) * 8);
-        c[k][0] = __ldg(q);
-        c[k][1] = __ldg(q + 1);
-      } else {
-        c[k][0] = c[k][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      acc[0] = fmaf(w[k], c[k][0].x, acc[0]);
-      acc[1] = fmaf(w[k], c[k][0].y, acc[1]);
-      acc[2] = fmaf(w[k], c[k][0].z, acc[2]);
-      acc[3] = fmaf(w[k], c[k][0].w, acc[3]);
-      acc[4] = fmaf(w[k], c[k][1].x, acc[4]);
-      acc[5] = fmaf(w[k], c[k][1].y, acc[5]);
-      acc[6] = fmaf(w[k], c[k][1].z, acc[6]);
-      acc[7] = fmaf(w[k], c[k][1].w, acc[7]);
-    }
+    float acc[8];
+    trilinear8(p.vol, p.D, p.Hv, p.Wv, __ldg(n), __ldg(n + 1), __ldg(n + 2), acc, p.vox_idx ? p.vox_idx + m * 3 : nullptr);
     if ((p.ldf & 3) == 0) {
       reinterpret_cast<float4*>(out)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
       reinterpret_cast<float4*>(out)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
@@ -138,51 +96,16 @@ __global__ void __launch_bounds__(32 * kGatherWarps) gather_fwd_kernel(GatherPar
   if (HAS_IMG) {
     const float* q = p.pts + m * 3;
     const float px = __ldg(q), py = __ldg(q + 1), pz = __ldg(q + 2);
-    const float wm1 = (float)(p.W - 1), hm1 = (float)(p.H - 1);
     for (int v = 0; v < p.V; ++v) {
-      const float* cm = s_cams + v * 24;
-      // utils.py:264  pts @ R^T + T   (matmul = fma chain, then a separately rounded add)
-      const float c0 = __fadd_rn(dot3(px, py, pz, cm[0], cm[1], cm[2]), cm[3]);
-      const float c1 = __fadd_rn(dot3(px, py, pz, cm[4], cm[5], cm[6]), cm[7]);
-      const float c2 = __fadd_rn(dot3(px, py, pz, cm[8], cm[9], cm[10]), cm[11]);
-      // utils.py:268  @ K^T
-      const float i0 = dot3(c0, c1, c2, cm[12], cm[13], cm[14]);
-      const float i1 = dot3(c0, c1, c2, cm[15], cm[16], cm[17]);
-      const float i2 = dot3(c0, c1, c2, cm[18], cm[19], cm[20]);
-      // utils.py:269  (xy / z + 0.0) / (W-1, H-1) ; utils.py:487  * 2.0 - 1.0
-      const float gx = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn(__fdiv_rn(i0, i2), 0.f), wm1), 2.f), 1.f);
-      const float gy = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn(__fdiv_rn(i1, i2), 0.f), hm1), 2.f), 1.f);
-      const float mask = (gx > -1.f && gx < 1.f && gy > -1.f && gy < 1.f) ? 1.f : 0.f;  // utils.py:496
-      // ATen grid_sampler_2d, border padding: unnormalize, clip to [0, size-1], floor
-      const float ix = safe_int_range(fminf(wm1, fmaxf(unnormalize(gx, p.W), 0.f)));
-      const float iy = safe_int_range(fminf(hm1, fmaxf(unnormalize(gy, p.H), 0.f)));
-      const float fx0 = floorf(ix), fy0 = floorf(iy);
-      const int x0 = (int)fx0, y0 = (int)fy0;
-      if (p.pix_idx) {
-        p.pix_idx[(m * p.V + v) * 2 + 0] = x0;
-        p.pix_idx[(m * p.V + v) * 2 + 1] = y0;
-      }
-      const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix;
-      const float wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
-      const float4* base = reinterpret_cast<const float4*>(p.img) + (int64_t)v * p.H * p.W;
-      const bool x0ok = (unsigned)x0 < (unsigned)p.W, x1ok = (unsigned)(x0 + 1) < (unsigned)p.W;
-      const bool y0ok = (unsigned)y0 < (unsigned)p.H, y1ok = (unsigned)(y0 + 1) < (unsigned)p.H;
-      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 a = (x0ok && y0ok) ? __ldg(base + (int64_t)y0 * p.W + x0) : z4;
-      const float4 b = (x1ok && y0ok) ? __ldg(base + (int64_t)y0 * p.W + x0 + 1) : z4;
-      const float4 c = (x0ok && y1ok) ? __ldg(base + (int64_t)(y0 + 1) * p.W + x0) : z4;
-      const float4 d = (x1ok && y1ok) ? __ldg(base + (int64_t)(y0 + 1) * p.W + x0 + 1) : z4;
-      const float wa = wx0 * wy0, wb = wx1 * wy0, wc = wx0 * wy1, wd = wx1 * wy1;
-      const float r = fmaf(wd, d.x, fmaf(wc, c.x, fmaf(wb, b.x, wa * a.x)));
-      const float g = fmaf(wd, d.y, fmaf(wc, c.y, fmaf(wb, b.y, wa * a.y)));
-      const float bl = fmaf(wd, d.z, fmaf(wc, c.z, fmaf(wb, b.z, wa * a.z)));
+      const float4 f = view_sample(reinterpret_cast<const float4*>(p.img) + (int64_t)v * p.H * p.W, p.H, p.W, s_cams + v * 24,
+                                   px, py, pz, p.pix_idx ? p.pix_idx + (m * p.V + v) * 2 : nullptr);
       if ((p.ldf & 3) == 0) {
-        reinterpret_cast<float4*>(out + 8)[v] = make_float4(r, g, bl, mask);
+        reinterpret_cast<float4*>(out + 8)[v] = f;
       } else {
-        out[8 + 4 * v] = r;
-        out[9 + 4 * v] = g;
-        out[10 + 4 * v] = bl;
-        out[11 + 4 * v] = mask;
+        out[8 + 4 * v] = f.x;
+        out[9 + 4 * v] = f.y;
+        out[10 + 4 * v] = f.z;
+        out[11 + 4 * v] = f.w;
       }
     }
   }

@@ -25,8 +25,10 @@
 // Shared memory therefore only holds the small per-tile inputs (PE, dirPE, feats: SS-form MMAs)
 // and a deep weight ring, and the MMA operand traffic out of shared memory is halved.
 //
-// Warp roles (320 threads): warps 0-7 prologue + epilogue (TMEM lane quarter = warp % 4, column
-// half = warp / 4), warp 8 = weight producer (cp.async.bulk / UBLKCP, weights pre-packed on the
+// Warp roles (384 threads): warps 0-7 epilogue (TMEM lane quarter = warp % 4, column half = warp / 4),
+// warps 10-11 loaders (two sample rows per thread: they gather the NEXT tile's features from the encoding
+// volume / source views, encode PE and stage everything as bf16 operands while the current tile is in
+// the tensor pipe), warp 8 = weight producer (cp.async.bulk / UBLKCP, weights pre-packed on the
 // host side of the ABI in the exact smem image, consumption order), warp 9 = MMA issuer + TMEM
 // owner.  The weight ring has 4 slots of 36 KB and every op consumes whole ring revolutions (the
 // plan pads with empty stages), so slot numbers, descriptors and barrier addresses in the issue
@@ -43,6 +45,7 @@
 #include <cstring>
 #include <vector>
 
+#include "gather_core.cuh"
 #include "net.cuh"
 #include "tc_ptx.cuh"
 
@@ -54,7 +57,9 @@ constexpr int kStages = 4;
 constexpr int kChunkBytes = kTile * 16;  // one 8-column k-chunk of a 128-row smem operand tile
 constexpr int kMaxPlan = 64;
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 32 * (kEpiWarps + 2);
+constexpr int kLoadWarps = 2;             // stage the next tile's inputs (gather + PE), two rows per thread
+constexpr int kThreads = 32 * (kEpiWarps + 2 + kLoadWarps);
+constexpr int kMaxViews = 14;             // 8 + 4 V <= 64 feature columns
 #define ACC_COL_OF(part) ((uint32_t)(part) * 128u)
 constexpr uint32_t GATE_COL = 256, HEAD_COL = 256, HEAD2_COL = 272, ACT_COL = 384;
 
@@ -82,6 +87,9 @@ struct TcParams {
   const float* ndc; int ndc_ld; int has_t; float t;
   const float* feats; int ldf;
   const float* dirs; int S;
+  // fused gather (vol != nullptr): the loader warps sample the encoding volume + source views themselves
+  const float* pts; const float* vol; int D, Hv, Wv; const float* img; int V, H, W; const float* cams;
+  float* feats_out; int ldfo;   // optional fp32 copy of the gathered features (the reference's input_feat)
   const float* x; int ldx;
   int P, Ppad, F, Fpad;
   int kind, out_ch, overlap;
@@ -271,7 +279,8 @@ __device__ __forceinline__ void mma_skip(MmaCtx& c) {
 template <int C, bool GATE32>  // C = 3 (static: xyz) or 4 (dynamic: xyz + t); GATE32: fp32 gate multiply
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_bars[2 * kStages + 6];
+  __shared__ __align__(8) uint64_t s_bars[2 * kStages + 9];
+  __shared__ float s_cams[kMaxViews * 24];
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -285,6 +294,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   Bars b;
   b.full = bars; b.empty = bars + 8 * kStages; b.acc_full = bars + 16 * kStages;
   b.acc_free = b.acc_full + 16; b.a_ready = b.acc_free + 16;
+  // loader handshake: inputs of tile #it staged (4 loader warps) / feats operand free (GATE retired) / PE operand free (L5 retired)
+  const uint32_t in_ready = b.a_ready + 16, feats_free = in_ready + 8, pe_free = in_ready + 16;
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { ptx::mbar_init(b.full + 8 * s, 1); ptx::mbar_init(b.empty + 8 * s, 1); }
@@ -293,11 +304,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       ptx::mbar_init(b.acc_free + 8 * i, kEpiWarps);
       ptx::mbar_init(b.a_ready + 8 * i, kEpiWarps);
     }
+    ptx::mbar_init(in_ready, kLoadWarps); ptx::mbar_init(feats_free, 1); ptx::mbar_init(pe_free, 1);
     ptx::fence_mbar_init();
   }
   if (tid < kTile) {  // the constant "ones" A chunk pair: columns 0, 1 = 1.0 (bias hi, lo), the rest 0
     ptx::st_smem_v4(s_base + ones_chunk * kChunkBytes + tid * 16, 0x3F803F80u, 0u, 0u, 0u);
     ptx::st_smem_v4(s_base + (ones_chunk + 1) * kChunkBytes + tid * 16, 0u, 0u, 0u, 0u);
+    ptx::fence_proxy_async_smem();
+  }
+  if (p.vol) {
+    for (int i = tid; i < p.V * 24; i += kThreads) s_cams[i] = __ldg(p.cams + i);
+    for (int i = tid; i < (p.Fpad / 8) * kTile; i += kThreads) ptx::st_smem_v4(s_base + feat_chunk * kChunkBytes + i * 16, 0u, 0u, 0u, 0u);
     ptx::fence_proxy_async_smem();
   }
   if (warp == kEpiWarps + 1) { ptx::tmem_alloc(ptx::smem_u32(&s_tmem), 512); ptx::tmem_relinquish(); }
@@ -350,9 +367,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     for (int64_t it = 0; it < my_tiles; ++it) {
       c.n_issued = 0;
       // ---- revolution 0: GATE (feats, SS) | L0 (PE, SS) ----
+      wait_bar(in_ready, (uint32_t)(it & 1), 210);   // the loader warps have staged this tile's operands
       c.next_op(); c.wait(15u);
       mma_stage<128, false, 0>(c, feat_lo, nk_f, acc0, true, true, 0);
       mma_stage<128, false, 1>(c, feat_lo, nk_f, acc1, true, true, 1);
+      if (ptx::elect_one()) ptx::mma_commit(feats_free);   // feats operand may be overwritten once GATE has retired
+      __syncwarp();
       c.next_op();
       if (!ov) c.wait(15u);
       c.wait(4u | 1u);   // every barrier of part X must be observed before the commit that lets X complete again
@@ -369,6 +389,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
           mma_stage<128, false, 0>(c, pe_lo, nk_p, acc0, true, false, -1);
           c.wait(8u);
           mma_stage<128, false, 1>(c, pe_lo, nk_p, acc1, true, false, -1);
+          if (ptx::elect_one()) ptx::mma_commit(pe_free);   // last reader of the PE operand
+          __syncwarp();
           c.wait(1u);
           mma_stage<128, true, 2>(c, act, 8, acc0, false, false, -1);
           mma_stage<128, true, 3>(c, act, 8, acc1, false, false, -1);
@@ -432,66 +454,135 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         __trap();
       }
     }
+  } else if (warp >= kEpiWarps + 2) {
+    // ===================== loader warps: stage the operands of the tiles, one tile ahead of the tensor pipe =====
+    // Two sample rows per thread.  feats (read by GATE only) and PE (last read by L5) are single buffers guarded by
+    // feats_free / pe_free (tcgen05.commit behind their last readers); dirPE (read by VIEWS at the very end of a
+    // tile) is double buffered by tile parity.
+    const int row0 = (warp - (kEpiWarps + 2)) * 32 + lane;   // this thread stages rows row0 and row0 + 64
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      if (it > 0) wait_bar(feats_free, (uint32_t)((it - 1) & 1), 400);
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int row = row0 + 64 * h;
+        const int64_t m = (blockIdx.x + it * gridDim.x) * kTile + row;
+        const bool valid = m < p.M;
+        // ---- gathered features: fused trilinear volume sample + per-view bilinear RGB + mask (gather_core.cuh),
+        //      or pre-gathered feats / the feat block of x.  The feats operand is free once GATE(it-1) has retired. ----
+        if (p.vol) {
+          // written straight into the bf16 operand (16 B for the 8 volume channels, 8 B per view) and, optionally,
+          // into the fp32 input_feat copy; the pad columns [F, Fpad) were zeroed once at start-up
+          const uint32_t frow = s_base + feat_chunk * kChunkBytes + row * 16;
+          float* o = p.feats_out ? p.feats_out + m * p.ldfo : nullptr;
+          const bool vec = (p.ldfo & 3) == 0;
+          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          float px = 0.f, py = 0.f, pz = 0.f;
+          if (valid) {
+            const float* n = p.ndc + m * p.ndc_ld;
+            trilinear8(p.vol, p.D, p.Hv, p.Wv, __ldg(n), __ldg(n + 1), __ldg(n + 2), acc);
+            const float* q = p.pts + m * 3;
+            px = __ldg(q); py = __ldg(q + 1); pz = __ldg(q + 2);
+            if (o) {
+              if (vec) {
+                reinterpret_cast<float4*>(o)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                reinterpret_cast<float4*>(o)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = acc[k];
+              }
+            }
+          }
+          ptx::st_smem_v4(frow, ptx::pack_bf16(acc[0], acc[1]), ptx::pack_bf16(acc[2], acc[3]), ptx::pack_bf16(acc[4], acc[5]),
+                          ptx::pack_bf16(acc[6], acc[7]));
+#pragma unroll 1
+          for (int v = 0; v < p.V; ++v) {
+            float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+              c4 = view_sample(reinterpret_cast<const float4*>(p.img) + (int64_t)v * p.H * p.W, p.H, p.W, s_cams + v * 24, px, py, pz);
+              if (o) {
+                if (vec) reinterpret_cast<float4*>(o + 8)[v] = c4;
+                else { o[8 + 4 * v] = c4.x; o[9 + 4 * v] = c4.y; o[10 + 4 * v] = c4.z; o[11 + 4 * v] = c4.w; }
+              }
+            }
+            ptx::st_smem_v2(frow + (uint32_t)(1 + (v >> 1)) * kChunkBytes + (uint32_t)(v & 1) * 8u, ptx::pack_bf16(c4.x, c4.y),
+                            ptx::pack_bf16(c4.z, c4.w));
+          }
+        } else {
+          float f[64];
+#pragma unroll
+          for (int i = 0; i < 64; ++i) f[i] = 0.f;
+          if (valid) {
+            const float* src = p.x ? (p.x + m * p.ldx + p.P) : (p.feats + m * p.ldf);
+#pragma unroll
+            for (int j = 0; j < 64; ++j) if (j < p.F) f[j] = __ldg(src + j);
+          }
+          if (p.Fpad <= 32) store_row_chunks<32>(s_base, feat_chunk, row, f);
+          else if (p.Fpad <= 48) store_row_chunks<48>(s_base, feat_chunk, row, f);
+          else store_row_chunks<64>(s_base, feat_chunk, row, f);
+        }
+      }
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int row = row0 + 64 * h;
+        const int64_t m = (blockIdx.x + it * gridDim.x) * kTile + row;
+        const bool valid = m < p.M;
+        // ---- direction PE (this tile parity's buffer: its last reader, VIEWS two tiles ago, retired long ago) ----
+        {
+          float d[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) d[i] = 0.f;
+          if (valid) {
+            if (p.x) {
+#pragma unroll
+              for (int j = 0; j < 27; ++j) d[j] = __ldg(p.x + m * p.ldx + p.P + p.F + j);
+            } else {
+              const float* dp = p.dirs + (m / p.S) * 3;
+              float v[4] = {__ldg(dp), __ldg(dp + 1), __ldg(dp + 2), 0.f};
+              pe_row<3, 4>(v, d);
+            }
+          }
+          store_row_chunks<32>(s_base, dir_chunk + 4 * (int)(it & 1), row, d);
+        }
+      }
+      if (it > 0) wait_bar(pe_free, (uint32_t)((it - 1) & 1), 401);
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int row = row0 + 64 * h;
+        const int64_t m = (blockIdx.x + it * gridDim.x) * kTile + row;
+        const bool valid = m < p.M;
+        // ---- point PE ----
+        {
+          float pe[C * 21 + 12];
+#pragma unroll
+          for (int i = 0; i < C * 21 + 12; ++i) pe[i] = 0.f;
+          if (valid) {
+            if (p.x) {
+#pragma unroll
+              for (int j = 0; j < C * 21; ++j) pe[j] = __ldg(p.x + m * p.ldx + j);  // already encoded (P = 21 C)
+            } else {
+              float v[4] = {__ldg(p.ndc + m * p.ndc_ld), __ldg(p.ndc + m * p.ndc_ld + 1), __ldg(p.ndc + m * p.ndc_ld + 2), p.t};
+              pe_row<C, 10>(v, pe);
+            }
+          }
+          if (C == 3) store_row_chunks<64>(s_base, 0, row, pe);
+          else store_row_chunks<96>(s_base, 0, row, pe);
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(in_ready);
+    }
   } else {
-    // ===================== prologue + epilogue warps =====================
+    // ===================== epilogue warps =====================
     const int q = warp & 3, hsel = warp >> 2;
     const int row = q * 32 + lane;
     uint32_t nfull[2] = {0, 0};
     int tl_n[2] = {0, 0}; (void)tl_n;
     const uint32_t tmem_lane = tmem + ((uint32_t)(q * 32) << 16);
-    // stage the inputs of tile number `it` of this CTA: warps 0-3 encode the point, warps 4-7 stage feats + direction
-    auto stage_inputs = [&](int64_t it) {
-      const int64_t m = (blockIdx.x + it * gridDim.x) * kTile + row;
-      const bool valid = m < p.M;
-      if (hsel == 0) {
-        float pe[C * 21 + 12];
-#pragma unroll
-        for (int i = 0; i < C * 21 + 12; ++i) pe[i] = 0.f;
-        if (valid) {
-          if (p.x) {
-#pragma unroll
-            for (int j = 0; j < C * 21; ++j) pe[j] = __ldg(p.x + m * p.ldx + j);  // already encoded (P = 21 C)
-          } else {
-            float v[4] = {__ldg(p.ndc + m * p.ndc_ld), __ldg(p.ndc + m * p.ndc_ld + 1), __ldg(p.ndc + m * p.ndc_ld + 2), p.t};
-            pe_row<C, 10>(v, pe);
-          }
-        }
-        if (C == 3) store_row_chunks<64>(s_base, 0, row, pe);
-        else store_row_chunks<96>(s_base, 0, row, pe);
-      } else {
-        float f[64];
-#pragma unroll
-        for (int i = 0; i < 64; ++i) f[i] = 0.f;
-        const float* src = p.x ? (p.x + m * p.ldx + p.P) : (p.feats + m * p.ldf);
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 64; ++j) if (j < p.F) f[j] = __ldg(src + j);
-        }
-        if (p.Fpad <= 32) store_row_chunks<32>(s_base, feat_chunk, row, f);
-        else if (p.Fpad <= 48) store_row_chunks<48>(s_base, feat_chunk, row, f);
-        else store_row_chunks<64>(s_base, feat_chunk, row, f);
-        float d[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) d[i] = 0.f;
-        if (valid) {
-          if (p.x) {
-#pragma unroll
-            for (int j = 0; j < 27; ++j) d[j] = __ldg(p.x + m * p.ldx + p.P + p.F + j);
-          } else {
-            const float* dp = p.dirs + (m / p.S) * 3;
-            float v[4] = {__ldg(dp), __ldg(dp + 1), __ldg(dp + 2), 0.f};
-            pe_row<3, 4>(v, d);
-          }
-        }
-        store_row_chunks<32>(s_base, dir_chunk + 4 * (int)(it & 1), row, d);
-      }
-      ptx::fence_proxy_async_smem();
-    };
-    if (my_tiles > 0) stage_inputs(0);
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t m = (blockIdx.x + it * gridDim.x) * kTile + row;
       const bool valid = m < p.M;
-      // the tile's inputs were staged during the previous tile (or just above): tell the MMA warp
+      // tile start: stands for "the previous tile's RGB epilogue is done" on all four epilogue -> MMA barriers
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -506,8 +597,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         epilogue_compute<3>(tmem_lane, part, hsel, b.acc_free + 8 * part, lane, pk);
         epilogue_store(tmem_lane + GATE_COL + part * 64 + hsel * 32, pk, b.a_ready + 8 * part, lane);
       }
-      // ---- L0..L7; once L5 has retired (last reader of PE; feats died with GATE) the NEXT tile's inputs are
-      //      staged in the idle time of the remaining epilogues ----
+      // ---- L0..L7 ----
       for (int l = 0; l < 8; ++l) {
 #ifdef ZEST_TC_TIMELINE
         const bool tl_on = p.tl && blockIdx.x == 0 && it == 3 && lane == 0;
@@ -526,7 +616,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
 #else
         epilogue_two_part<GATE32 ? 4 : 0>(tmem_lane, hsel, b, nfull, lane);
 #endif
-        if (l == 5 && it + 1 < my_tiles) stage_inputs(it + 1);
       }
       // ---- FEAT + heads: the head accumulators (sigma + blend / scene flow / probs) are complete with
       //      FEAT part 0's commit; they are read into registers here, long before the next tile's
@@ -855,6 +944,25 @@ extern "C" int zest_mlp_fwd_tc(const zest_net* net, const float* ndc, int ndc_ld
   TcParams p{};
   p.ndc = ndc; p.ndc_ld = ndc_ld; p.has_t = has_t; p.t = t; p.feats = feats; p.ldf = ldf; p.dirs = dirs; p.S = S;
   p.x = nullptr; p.ldx = 0; p.M = M; p.raw = raw;
+  return tc_launch(net, p, (cudaStream_t)stream);
+}
+
+extern "C" int zest_gather_mlp_fwd_tc(const zest_net* net, const float* rays_pts, const float* rays_ndc, int ndc_ld, int has_t,
+                                      float t, const float* vol_cl, int D, int Hv, int Wv, const float* img_cl, int V, int H,
+                                      int W, const float* cams, const float* dirs, int S, int64_t M, float* feats_out, int ldfo,
+                                      float* raw, void* stream) {
+  ZEST_CHECK_ARG(net && rays_pts && rays_ndc && vol_cl && img_cl && cams && dirs && raw && M >= 0 && S > 0 && ndc_ld >= 3,
+                 "zest_gather_mlp_fwd_tc: bad arguments");
+  ZEST_CHECK_ARG((has_t != 0) == (net->in_pts == 84), "zest_gather_mlp_fwd_tc: has_t does not match the net's input width");
+  ZEST_CHECK_ARG(V > 0 && V <= kMaxViews && net->in_feat == 8 + 4 * V, "zest_gather_mlp_fwd_tc: net expects %d feature columns, 8 + 4 x %d views given",
+                 net->in_feat, V);
+  ZEST_CHECK_ARG(D > 0 && Hv > 0 && Wv > 0 && H > 0 && W > 0, "zest_gather_mlp_fwd_tc: bad volume / image sizes");
+  ZEST_CHECK_ARG(!feats_out || ldfo >= net->in_feat, "zest_gather_mlp_fwd_tc: ldfo too small");
+  TcParams p{};
+  p.ndc = rays_ndc; p.ndc_ld = ndc_ld; p.has_t = has_t; p.t = t; p.dirs = dirs; p.S = S;
+  p.pts = rays_pts; p.vol = vol_cl; p.D = D; p.Hv = Hv; p.Wv = Wv; p.img = img_cl; p.V = V; p.H = H; p.W = W; p.cams = cams;
+  p.feats_out = feats_out; p.ldfo = ldfo;
+  p.M = M; p.raw = raw;
   return tc_launch(net, p, (cudaStream_t)stream);
 }
 

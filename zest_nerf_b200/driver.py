@@ -40,10 +40,8 @@ class FrameRenderer:
         self.net_static, self.net_dynamic = net_static, net_dynamic
         self.n_samples, self.pad = n_samples, pad
         self.frame = None
-        # side stream: the dynamic net's gather (latency-bound, ~1 small CTA per SM fits next to the persistent
-        # MLP CTA) runs underneath the static net's tensor-core MLP instead of in front of the dynamic one
-        self.overlap_gather = os.environ.get("ZEST_GATHER_OVERLAP", "1") != "0"
-        self._side = None
+        # bf16 inference: gather + PE + MLP in one launch per net (ZEST_FUSED_GATHER=0: separate gather kernel)
+        self.fused = os.environ.get("ZEST_FUSED_GATHER", "1") != "0"
 
     # ------------------------------------------------------------------ per time-frame state
     def set_frame(self, vol_static, imgs, im_cam_mat, vol_dynamic=None, nb_imgs=None, nb_cam_mat=None, src=0,
@@ -94,44 +92,29 @@ class FrameRenderer:
         dyn = fr["dynamic"] and self.net_dynamic is not None
         cos, dirs_s = ops.dirfeat(rays_dir, fr["cams_s"])
         pk_s, _ = ops.packed(self.net_static)
-        F_s = 8 + 4 * fr["V"]
-        feats_s = ops.gather_fwd(pts, ndc, fr["vol_s"], fr["img"], fr["cams_s"], R, S, F_s)
-        tick("gather_s")
-        side = None
-        if dyn:
-            pk_d, _ = ops.packed(self.net_dynamic)
-            F_d = 8 + 4 * fr["NB"]
-            if self.overlap_gather and bf16:
-                if self._side is None:
-                    self._side = torch.cuda.Stream(device=self.device, priority=0)
-                side, main = self._side, torch.cuda.current_stream()
-                ready = torch.cuda.Event()
-                ready.record(main)
-        raw_s = ops.mlp_tc(pk_s, ndc, None, feats_s, dirs_s, S) if bf16 else \
-            ops.mlp_f32(pk_s, ops.encode_fwd(ndc, None, 10, feats_s, dirs_s, 4, S))
-        if side is not None:   # enqueued after the MLP so that the MLP's CTAs are placed first
-            side.wait_event(ready)
-            with torch.cuda.stream(side):
-                _, dirs_d = ops.dirfeat(rays_dir, fr["cams_d"])
-                feats_d = ops.gather_fwd(pts, ndc, fr["vol_d"], fr["nb"], fr["cams_d"], R, S, F_d)
-                done = torch.cuda.Event()
-                done.record(side)
-            for t_ in (pts, ndc, rays_dir, feats_d, dirs_d):
-                t_.record_stream(side)
+        fused = bf16 and self.fused and fr["V"] <= ops.FUSED_MAX_VIEWS
+        if fused:     # one launch per net: gather + PE + tensor-core MLP
+            raw_s, _ = ops.gather_mlp_tc(pk_s, pts, ndc, None, fr["vol_s"], fr["img"], fr["cams_s"], dirs_s, R, S)
+        else:
+            feats_s = ops.gather_fwd(pts, ndc, fr["vol_s"], fr["img"], fr["cams_s"], R, S, 8 + 4 * fr["V"])
+            tick("gather_s")
+            raw_s = ops.mlp_tc(pk_s, ndc, None, feats_s, dirs_s, S) if bf16 else \
+                ops.mlp_f32(pk_s, ops.encode_fwd(ndc, None, 10, feats_s, dirs_s, 4, S))
         tick("mlp_s")
         rgb, depth, _, _ = ops.composite_static(raw_s, z, cos, None, R, S, False, want_per_sample=False)
         out = {"rgb_map": rgb.view(1, R, 3), "depth_map": depth.view(1, R)}
         tick("comp_s")
         if dyn:
-            if side is not None:
-                torch.cuda.current_stream().wait_event(done)
-            else:
-                _, dirs_d = ops.dirfeat(rays_dir, fr["cams_d"])
-                feats_d = ops.gather_fwd(pts, ndc, fr["vol_d"], fr["nb"], fr["cams_d"], R, S, F_d)
-            tick("gather_d")
+            _, dirs_d = ops.dirfeat(rays_dir, fr["cams_d"])
+            pk_d, _ = ops.packed(self.net_dynamic)
             t = float(ref_frame_idx)
-            raw_d = ops.mlp_tc(pk_d, ndc, t, feats_d, dirs_d, S) if bf16 else \
-                ops.mlp_f32(pk_d, ops.encode_fwd(ndc, t, 10, feats_d, dirs_d, 4, S))
+            if fused and fr["NB"] <= ops.FUSED_MAX_VIEWS:
+                raw_d, _ = ops.gather_mlp_tc(pk_d, pts, ndc, t, fr["vol_d"], fr["nb"], fr["cams_d"], dirs_d, R, S)
+            else:
+                feats_d = ops.gather_fwd(pts, ndc, fr["vol_d"], fr["nb"], fr["cams_d"], R, S, 8 + 4 * fr["NB"])
+                tick("gather_d")
+                raw_d = ops.mlp_tc(pk_d, ndc, t, feats_d, dirs_d, S) if bf16 else \
+                    ops.mlp_f32(pk_d, ops.encode_fwd(ndc, t, 10, feats_d, dirs_d, 4, S))
             tick("mlp_d")
             a, b, c, d, e, _ = ops.composite_blend(raw_d, raw_s, z, cos, None, R, S, want_per_sample=False)
             out.update({"rgb_map_ref": a.view(1, R, 3), "depth_map_ref": b.view(1, R), "rgb_map_ref_dy": c.view(1, R, 3),

@@ -16,6 +16,7 @@ from . import _lib
 _MLP_MODE = "bf16"   # "bf16": tcgen05 tensor cores (inference default); "fp32": CUDA-core reference path
 _T_STOP = 0.0        # early-termination threshold of the composite kernels (0 = exact reference)
 F32_ROWS_PER_CALL = 1 << 20
+FUSED_MAX_VIEWS = 14   # zest_gather_mlp_fwd_tc: 8 + 4 V <= 64 feature columns
 
 
 def set_mlp_mode(mode: str):
@@ -245,6 +246,21 @@ def mlp_tc(pk, ndc, t, feats, dirs, S):
                                            _ptr(feats), feats.shape[1], _ptr(dirs), S, M, _ptr(raw), _stream()),
                "zest_mlp_fwd_tc")
     return raw
+
+
+def gather_mlp_tc(pk, rays_pts, ndc, t, vol_cl, img_cl, cams, dirs, R, S, want_feats=False):
+    """The fused hot path: feature gather + PE + tensor-core MLP in one launch.  Returns (raw, feats | None)."""
+    M = R * S
+    D, Hv, Wv = vol_cl.shape[:3]
+    V, H, W = img_cl.shape[:3]
+    F = 8 + 4 * V
+    raw = torch.empty((M, pk.out_ch), device=ndc.device, dtype=torch.float32)
+    feats = torch.empty((M, F), device=ndc.device, dtype=torch.float32) if want_feats else None
+    _lib.check(_lib.load().zest_gather_mlp_fwd_tc(pk.handle, _ptr(rays_pts), _ptr(ndc), ndc.shape[1], int(t is not None),
+                                                  float(t or 0.0), _ptr(vol_cl), D, Hv, Wv, _ptr(img_cl), V, H, W, _ptr(cams),
+                                                  _ptr(dirs), S, M, _ptr(feats), F, _ptr(raw), _stream()),
+               "zest_gather_mlp_fwd_tc")
+    return raw, feats
 
 
 def mlp_tc_x(pk, x):

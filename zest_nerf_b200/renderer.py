@@ -94,11 +94,14 @@ def rendering(args, rays_pts, rays_ndc, depth_candidates, rays_dir,
             rgb_map, depth_map, weights, alpha = ops.CompositeStaticFn.apply(raw_s, z, cos, noise_s, R, S, bool(white_bkgd))
         else:
             vol_s = ops.pack_volume(volume_feature_static)
-            feats_s = ops.gather_fwd(pts, ndc, vol_s, img_cl, cams_s, R, S, F_s)
-            if ops.get_mlp_mode() == "bf16":
-                raw_s = ops.mlp_tc(pk_s, ndc, None, feats_s, dirs_s, S)
+            if ops.get_mlp_mode() == "bf16" and V <= ops.FUSED_MAX_VIEWS:   # one launch: gather + PE + tensor-core MLP
+                raw_s, feats_s = ops.gather_mlp_tc(pk_s, pts, ndc, None, vol_s, img_cl, cams_s, dirs_s, R, S, want_feats=True)
             else:
-                raw_s = ops.mlp_f32(pk_s, ops.encode_fwd(ndc, None, nf_p, feats_s, dirs_s, nf_d, S))
+                feats_s = ops.gather_fwd(pts, ndc, vol_s, img_cl, cams_s, R, S, F_s)
+                if ops.get_mlp_mode() == "bf16":
+                    raw_s = ops.mlp_tc(pk_s, ndc, None, feats_s, dirs_s, S)
+                else:
+                    raw_s = ops.mlp_f32(pk_s, ops.encode_fwd(ndc, None, nf_p, feats_s, dirs_s, nf_d, S))
             rgb_map, depth_map, weights, alpha = ops.composite_static(raw_s, z, cos, noise_s, R, S, white_bkgd)
         raw_s3 = raw_s.view(1, R, S, -1)
         ret = {"rgb_map": rgb_map.view(1, R, 3), "depth_map": depth_map.view(1, R),
@@ -125,11 +128,14 @@ def rendering(args, rays_pts, rays_ndc, depth_candidates, rays_dir,
 
         if not train:
             vol_d = ops.pack_volume(volume_feature_dynamic)
-            feats_d = ops.gather_fwd(pts, ndc, vol_d, nb_cl, cams_d, R, S, F_d)
-            if ops.get_mlp_mode() == "bf16":
-                raw_d = ops.mlp_tc(pk_d, ndc, t_ref, feats_d, dirs_d, S)
+            if ops.get_mlp_mode() == "bf16" and NB <= ops.FUSED_MAX_VIEWS:
+                raw_d, _ = ops.gather_mlp_tc(pk_d, pts, ndc, t_ref, vol_d, nb_cl, cams_d, dirs_d, R, S)
             else:
-                raw_d = ops.mlp_f32(pk_d, ops.encode_fwd(ndc, t_ref, nf_p, feats_d, dirs_d, nf_d, S))
+                feats_d = ops.gather_fwd(pts, ndc, vol_d, nb_cl, cams_d, R, S, F_d)
+                if ops.get_mlp_mode() == "bf16":
+                    raw_d = ops.mlp_tc(pk_d, ndc, t_ref, feats_d, dirs_d, S)
+                else:
+                    raw_d = ops.mlp_f32(pk_d, ops.encode_fwd(ndc, t_ref, nf_p, feats_d, dirs_d, nf_d, S))
             noise_b = torch.randn((R, S), device=dev) * raw_noise_std if raw_noise_std > 0 else None
             out = ops.composite_blend(raw_d, raw_s, z, cos, noise_b, R, S, want_per_sample=not val)
         else:
