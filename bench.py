@@ -251,8 +251,16 @@ def main():
     flops = 2.0 * (m_s + m_d) * R * S
     achieved = flops / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
     peak = pk["bf16_tflops_sustained"]
+    traffic = None   # dram__bytes_read + write per launch of the dominant kernel, from the committed ncu capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.config)
+        if tj and args.mlp == "bf16":
+            per = [v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in tj.items() if k.endswith("_net")]
+            traffic = sum(per) / len(per)
+    except Exception:
+        traffic = None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "mlp_tc_kernel (2 launches/step: static + dynamic net; the feature gather runs inside it)",
+                "traffic": traffic, "traffic_note": "mean DRAM bytes per mlp_tc_kernel launch (ncu --set full, profiles/ncu_traffic.json)", "kernel": "mlp_tc_kernel (2 launches/step: static + dynamic net; the feature gather runs inside it)",
                 "peak_source": f"bf16_tflops_sustained, {src}", "mlp_ms_per_step": mlp_ms,
                 "whole_step_frac": flops / (total_ms / args.steps * 1e-3) / 1e12 / peak,
                 "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()}}
