@@ -57,7 +57,9 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi at 50 ms; stop(t0, t1) reports the median SM clock / power of the samples taken inside the
+    timed region [t0, t1] (time.time() stamps) and every throttle reason seen there."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
@@ -67,29 +69,31 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
         except Exception:
             pass
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc:
             self.proc.terminate()
-        sm, reasons, mx = [], set(), 0
-        for r in self.rows:
+        sm, pw, reasons, mx = [], [], set(), 0
+        for ts, r in self.rows:
             try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                clk, cmax, p = float(r[1]), float(r[2]), float(r[3])
             except Exception:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+            mx = max(mx, cmax)
+            if t0 is not None and not (t0 <= ts <= t1 + 0.05):
+                continue
+            sm.append(clk); pw.append(p)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        sm.sort()
-        # "under load" = upper half of the samples (idle samples before/after the timed loop are dropped)
-        load = sm[len(sm) // 2:] if sm else []
-        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        sm.sort(); pw.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "power_w": pw[len(pw) // 2] if pw else None, "samples": len(sm)}
 
 
 def cpu_reference(cfg, n_rays, repeats, threads=None):
@@ -223,6 +227,7 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     stage_ev = []
     barrier()
+    t_wall0 = time.time()
     for k in range(args.steps):
         big.zero_()
         timers = []
@@ -231,13 +236,14 @@ def main():
         ev[k][1].record()
         stage_ev.append(timers)
     barrier()
+    t_wall1 = time.time()
     launches = lib.zest_launch_count() - launches0
     ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([sum(ms)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms)
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_wall0, t_wall1)
     value = world * R * args.steps / (total_ms * 1e-3)
 
     # stage breakdown + roofline of the dominant kernel (the tensor-core MLP launches)

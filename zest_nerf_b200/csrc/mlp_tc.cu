@@ -157,48 +157,58 @@ struct Bars {
 // MODE 1: acc -> bf16 pairs                      (FEAT)
 // MODE 2: acc, relu -> bf16 pairs                (VIEWS)
 // MODE 3: acc -> bf16 pairs                      (GATE; stored to the gate columns)
-// Loads the thread's 64 accumulator columns, releases the accumulator, returns 32 packed pairs.
+// A thread owns two 32-column runs of the part's 128 columns: sub-half 0 = [hsel*32, +32) and sub-half 1 =
+// [64 + hsel*32, +32), so that the eight warps together finish columns 0..63 first: those are K columns 0..63 of the
+// next layer's input and get their own a_ready barrier (the next layer's first four UMMAs start half an epilogue earlier).
 template <int MODE>
-__device__ __forceinline__ void epilogue_compute(uint32_t tmem_lane, int part, int hsel, uint32_t bar_free, int lane,
-                                                 uint32_t (&packed)[32], long long* t_ld = nullptr) {
-  uint32_t acc[2][32];
-  ptx::tmem_ld32(tmem_lane + ACC_COL_OF(part) + hsel * 64, acc[0]);
-  ptx::tmem_ld32(tmem_lane + ACC_COL_OF(part) + hsel * 64 + 32, acc[1]);
-  uint32_t g[2][16];
-  if (MODE == 0 || MODE == 4) {
-    ptx::tmem_ld16(tmem_lane + GATE_COL + part * 64 + hsel * 32, g[0]);
-    ptx::tmem_ld16(tmem_lane + GATE_COL + part * 64 + hsel * 32 + 16, g[1]);
+__device__ __forceinline__ void epi_math(const uint32_t (&acc)[32], const uint32_t (&g)[16], uint32_t (&packed)[16]) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    float v0 = __uint_as_float(acc[j]), v1 = __uint_as_float(acc[j + 1]);
+    if (MODE == 4) {
+      const uint32_t g01 = g[j / 2];
+      ptx::mul_f32x2(v0, v1, ptx::bf16_lo(g01), ptx::bf16_hi(g01));
+    }
+    uint32_t pk = ptx::pack_bf16(v0, v1);
+    if (MODE == 0) pk = ptx::mul_relu_bf16x2(pk, g[j / 2]);
+    if (MODE == 4 || MODE == 2) pk = ptx::relu_bf16x2(pk);
+    packed[j / 2] = pk;
   }
+}
+
+// out_base: TMEM column base of the destination (ACT_COL or GATE_COL).  bar_free: arrive once the accumulator is in
+// registers.  bar_rdy0 / bar_rdy1: arrive after sub-half 0 / 1 has landed (pass the same barrier twice -> arrive once, at the end).
+template <int MODE>
+__device__ __forceinline__ void epilogue_part(uint32_t tmem_lane, int part, int hsel, uint32_t out_base, uint32_t bar_free,
+                                              uint32_t bar_rdy0, uint32_t bar_rdy1, int lane, long long* t_ld = nullptr) {
+  const uint32_t acc_t = tmem_lane + ACC_COL_OF(part) + hsel * 32;
+  const uint32_t gate_t = tmem_lane + GATE_COL + part * 64 + hsel * 16;
+  const uint32_t out_t = tmem_lane + out_base + part * 64 + hsel * 16;
+  uint32_t acc[2][32], g[2][16], pk[16];
+  ptx::tmem_ld32(acc_t, acc[0]);
+  if (MODE == 0 || MODE == 4) ptx::tmem_ld16(gate_t, g[0]);
+  ptx::tmem_ld32(acc_t + 64, acc[1]);
+  if (MODE == 0 || MODE == 4) ptx::tmem_ld16(gate_t + 32, g[1]);
   ptx::tc_wait_ld();
   if (t_ld) *t_ld = clock64();
   // the accumulator half is drained: the MMA warp may overwrite it
   ptx::tc_fence_before();
   __syncwarp();
   if (lane == 0) ptx::mbar_arrive(bar_free);
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      float v0 = __uint_as_float(acc[h][j]), v1 = __uint_as_float(acc[h][j + 1]);
-      if (MODE == 4) {
-        const uint32_t g01 = g[h][j / 2];
-        ptx::mul_f32x2(v0, v1, ptx::bf16_lo(g01), ptx::bf16_hi(g01));
-      }
-      uint32_t pk = ptx::pack_bf16(v0, v1);
-      if (MODE == 0) pk = ptx::mul_relu_bf16x2(pk, g[h][j / 2]);
-      if (MODE == 4 || MODE == 2) pk = ptx::relu_bf16x2(pk);
-      packed[h * 16 + j / 2] = pk;
-    }
+  epi_math<MODE>(acc[0], g[0], pk);
+  ptx::tmem_st16(out_t, pk);
+  if (bar_rdy0 != bar_rdy1) {
+    ptx::tc_wait_st();
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(bar_rdy0);
   }
-}
-
-// store 32 packed pairs (= 64 bf16 columns) of this thread's row into TMEM columns [col, col + 32)
-__device__ __forceinline__ void epilogue_store(uint32_t taddr, const uint32_t (&packed)[32], uint32_t bar_ready, int lane) {
-  ptx::tmem_st32(taddr, packed);
+  epi_math<MODE>(acc[1], g[1], pk);
+  ptx::tmem_st16(out_t + 32, pk);
   ptx::tc_wait_st();
   ptx::tc_fence_before();
   __syncwarp();
-  if (lane == 0) ptx::mbar_arrive(bar_ready);
+  if (lane == 0) ptx::mbar_arrive(bar_rdy1);
 }
 
 __device__ __forceinline__ void arrive_idle(uint32_t bar_free, uint32_t bar_ready, int lane) {
@@ -206,17 +216,16 @@ __device__ __forceinline__ void arrive_idle(uint32_t bar_free, uint32_t bar_read
   if (lane == 0) { ptx::mbar_arrive(bar_free); ptx::mbar_arrive(bar_ready); }
 }
 
-// two-part hidden op (L0..L7): part p's outputs are K half p of the next layer's input, stored in place
+// two-part hidden op (L0..L7, FEAT): part p's outputs are K half p of the next layer's input, stored in place.
+// a_ready: [0] = K columns 0..63, [2] = 64..127 (part 0's two sub-halves), [1] = 128..255 (part 1).
 template <int MODE>
-__device__ __forceinline__ void epilogue_two_part(uint32_t tmem_lane, int hsel, const Bars& b, uint32_t (&nfull)[2], int lane) {
-#pragma unroll
-  for (int part = 0; part < 2; ++part) {
-    uint32_t pk[32];
-    wait_bar(b.acc_full + 8 * part, nfull[part]++ & 1, 310 + part);
-    ptx::tc_fence_after();
-    epilogue_compute<MODE>(tmem_lane, part, hsel, b.acc_free + 8 * part, lane, pk);
-    epilogue_store(tmem_lane + ACT_COL + part * 64 + hsel * 32, pk, b.a_ready + 8 * part, lane);
-  }
+__device__ __forceinline__ void epilogue_two_part(uint32_t tmem_lane, int hsel, const Bars& b, uint32_t (&nfull)[2], int lane, int tag) {
+  wait_bar(b.acc_full, nfull[0]++ & 1, tag);
+  ptx::tc_fence_after();
+  epilogue_part<MODE>(tmem_lane, 0, hsel, ACT_COL, b.acc_free, b.a_ready, b.a_ready + 16, lane);
+  wait_bar(b.acc_full + 8, nfull[1]++ & 1, tag + 1);
+  ptx::tc_fence_after();
+  epilogue_part<MODE>(tmem_lane, 1, hsel, ACT_COL, b.acc_free + 8, b.a_ready + 8, b.a_ready + 8, lane);
 }
 
 // ---- MMA issue helpers (warp-convergent; every operand warp-uniform; one elected lane issues) ------
@@ -234,6 +243,7 @@ struct MmaCtx {
     if (need & 2u) wait_bar(b.a_ready + 8, par, 201);
     if (need & 4u) wait_bar(b.acc_free, par, 202);
     if (need & 8u) wait_bar(b.acc_free + 8, par, 203);
+    if (need & 16u) wait_bar(b.a_ready + 16, par, 204);
   }
   __device__ __forceinline__ void end_revolution() { phase ^= 1u; }
 };
@@ -243,14 +253,28 @@ struct MmaCtx {
 //   bias: + one step against the ones chunk (the stage image carries the bias block after the weights)
 //   commit_part >= 0: the accumulator group ends here -> commit acc_full[commit_part]
 template <int N, bool TS, int SLOT>
-__device__ __forceinline__ void mma_stage(MmaCtx& c, uint32_t a, int n_k16, uint32_t d_tmem, bool first, bool bias, int commit_part) {
+__device__ __forceinline__ void mma_stage(MmaCtx& c, uint32_t a, int n_k16, uint32_t d_tmem, bool first, bool bias, int commit_part,
+                                          uint32_t mid_need = 0u) {
   constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
   wait_bar(c.b.full + 8 * SLOT, c.phase, 220 + SLOT);
   ptx::tc_fence_after();
   // B descriptor low word; one K = 16 step advances B by 2 chunks of N rows x 16 B
   uint32_t b_lo = (c.ring_lo + SLOT * (kStageBytes >> 4)) | ((uint32_t)N << 16);
+  uint32_t acc = first ? 0u : 1u;
+  if (mid_need) {   // first half of the K steps now, the rest once `mid_need` has been observed
+    const int h = n_k16 / 2;
+    if (ptx::elect_one()) {
+#pragma unroll 4
+      for (int k = 0; k < h; ++k) {
+        if (TS) ptx::mma_bf16_ts(d_tmem, a + (TS ? 8u : ((2u * kChunkBytes) >> 4)) * k, kHi | (b_lo + 2u * N * k), kIdesc, k ? 1u : acc);
+        else ptx::mma_bf16_ss(d_tmem, kHi | (a + ((2u * kChunkBytes) >> 4) * k), kHi | (b_lo + 2u * N * k), kIdesc, k ? 1u : acc);
+      }
+    }
+    __syncwarp();
+    a += (TS ? 8u : ((2u * kChunkBytes) >> 4)) * h; b_lo += 2u * N * h; n_k16 -= h; acc = 1u;
+    c.wait(mid_need);
+  }
   if (ptx::elect_one()) {
-    uint32_t acc = first ? 0u : 1u;
 #pragma unroll 8
     for (int k = 0; k < n_k16; ++k) {
       if (TS) ptx::mma_bf16_ts(d_tmem, a, kHi | b_lo, kIdesc, acc);
@@ -279,7 +303,7 @@ __device__ __forceinline__ void mma_skip(MmaCtx& c) {
 template <int C, bool GATE32>  // C = 3 (static: xyz) or 4 (dynamic: xyz + t); GATE32: fp32 gate multiply
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_bars[2 * kStages + 9];
+  __shared__ __align__(8) uint64_t s_bars[2 * kStages + 10];
   __shared__ float s_cams[kMaxViews * 24];
   __shared__ uint32_t s_tmem;
 
@@ -295,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   b.full = bars; b.empty = bars + 8 * kStages; b.acc_full = bars + 16 * kStages;
   b.acc_free = b.acc_full + 16; b.a_ready = b.acc_free + 16;
   // loader handshake: inputs of tile #it staged (4 loader warps) / feats operand free (GATE retired) / PE operand free (L5 retired)
-  const uint32_t in_ready = b.a_ready + 16, feats_free = in_ready + 8, pe_free = in_ready + 16;
+  const uint32_t in_ready = b.a_ready + 24, feats_free = in_ready + 8, pe_free = in_ready + 16;
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { ptx::mbar_init(b.full + 8 * s, 1); ptx::mbar_init(b.empty + 8 * s, 1); }
@@ -304,6 +328,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       ptx::mbar_init(b.acc_free + 8 * i, kEpiWarps);
       ptx::mbar_init(b.a_ready + 8 * i, kEpiWarps);
     }
+    ptx::mbar_init(b.a_ready + 16, kEpiWarps);
     ptx::mbar_init(in_ready, kLoadWarps); ptx::mbar_init(feats_free, 1); ptx::mbar_init(pe_free, 1);
     ptx::fence_mbar_init();
   }
@@ -368,14 +393,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       c.n_issued = 0;
       // ---- revolution 0: GATE (feats, SS) | L0 (PE, SS) ----
       wait_bar(in_ready, (uint32_t)(it & 1), 210);   // the loader warps have staged this tile's operands
-      c.next_op(); c.wait(15u);
+      c.next_op(); c.wait(31u);
       mma_stage<128, false, 0>(c, feat_lo, nk_f, acc0, true, true, 0);
       mma_stage<128, false, 1>(c, feat_lo, nk_f, acc1, true, true, 1);
       if (ptx::elect_one()) ptx::mma_commit(feats_free);   // feats operand may be overwritten once GATE has retired
       __syncwarp();
       c.next_op();
-      if (!ov) c.wait(15u);
-      c.wait(4u | 1u);   // every barrier of part X must be observed before the commit that lets X complete again
+      if (!ov) c.wait(31u);
+      c.wait(4u | 1u | 16u);   // every barrier of part X must be observed before the commit that lets X complete again
       mma_stage<128, false, 2>(c, pe_lo, nk_p, acc0, true, true, 0);
       c.wait(8u | 2u);
       mma_stage<128, false, 3>(c, pe_lo, nk_p, acc1, true, true, 1);
@@ -383,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       // ---- L1..L7: (p0, K lo) (p1, K lo) (p0, K hi) (p1, K hi); L5 = [pe | h4] starts with the PE blocks (smem) ----
       for (int l = 1; l < 8; ++l) {
         c.next_op();
-        if (!ov) c.wait(15u);
+        if (!ov) c.wait(31u);
         if (l == 5) {
           c.wait(4u);
           mma_stage<128, false, 0>(c, pe_lo, nk_p, acc0, true, false, -1);
@@ -392,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
           if (ptx::elect_one()) ptx::mma_commit(pe_free);   // last reader of the PE operand
           __syncwarp();
           c.wait(1u);
-          mma_stage<128, true, 2>(c, act, 8, acc0, false, false, -1);
+          mma_stage<128, true, 2>(c, act, 8, acc0, false, false, -1, 16u);
           mma_stage<128, true, 3>(c, act, 8, acc1, false, false, -1);
           c.end_revolution();
           c.wait(2u);
@@ -407,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
 #endif
           c.wait(4u | 1u);
           TL(9, 100 * l + 50);
-          mma_stage<128, true, 0>(c, act, 8, acc0, true, false, -1);
+          mma_stage<128, true, 0>(c, act, 8, acc0, true, false, -1, 16u);
           TL(9, 100 * l + 51);
           c.wait(8u);
           TL(9, 100 * l + 52);
@@ -424,9 +449,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       }
       // ---- FEAT (h7 -> feature); the N = 16 heads (same input; the gate columns are dead) ride behind the low-K stages ----
       c.next_op();
-      if (!ov) c.wait(15u);
+      if (!ov) c.wait(31u);
       c.wait(4u | 1u);
-      mma_stage<128, true, 0>(c, act, 8, acc0, true, false, -1);
+      mma_stage<128, true, 0>(c, act, 8, acc0, true, false, -1, 16u);
       c.wait(8u);
       mma_stage<128, true, 1>(c, act, 8, acc1, true, false, -1);
       c.wait(2u);
@@ -436,14 +461,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       mma_stage<128, true, 0>(c, act + 64, 8, acc1, false, true, 1);
       // ---- VIEWS: [feature (TMEM) | dirPE (smem)] -> acc0 (N = 128, single part); RGB (N = 16) from v ----
       c.next_op();
-      if (!ov) c.wait(15u);
+      if (!ov) c.wait(31u);
       c.wait(4u | 1u);
-      mma_stage<128, true, 1>(c, act, 8, acc0, true, false, -1);
+      mma_stage<128, true, 1>(c, act, 8, acc0, true, false, -1, 16u);
       c.wait(2u | 8u);
       mma_stage<128, true, 2>(c, act + 64, 8, acc0, false, false, -1);
       mma_stage<128, false, 3>(c, dir_lo[it & 1], 2, acc0, false, true, 0);
       c.end_revolution();
-      c.next_op(); c.wait(15u);
+      c.next_op(); c.wait(31u);
       mma_stage<16, true, 0>(c, act, 8, tmem + HEAD2_COL, true, true, 0);
       mma_skip<1>(c);
       mma_skip<2>(c);
@@ -587,34 +612,31 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       __syncwarp();
       if (lane == 0) {
         ptx::mbar_arrive(b.acc_free); ptx::mbar_arrive(b.acc_free + 8);
-        ptx::mbar_arrive(b.a_ready); ptx::mbar_arrive(b.a_ready + 8);
+        ptx::mbar_arrive(b.a_ready); ptx::mbar_arrive(b.a_ready + 8); ptx::mbar_arrive(b.a_ready + 16);
       }
       // ---- GATE: bf16 pairs -> gate columns ----
       for (int part = 0; part < 2; ++part) {
-        uint32_t pk[32];
         wait_bar(b.acc_full + 8 * part, nfull[part]++ & 1, 300 + part);
         ptx::tc_fence_after();
-        epilogue_compute<3>(tmem_lane, part, hsel, b.acc_free + 8 * part, lane, pk);
-        epilogue_store(tmem_lane + GATE_COL + part * 64 + hsel * 32, pk, b.a_ready + 8 * part, lane);
+        if (part == 0) epilogue_part<3>(tmem_lane, 0, hsel, GATE_COL, b.acc_free, b.a_ready, b.a_ready + 16, lane);
+        else epilogue_part<3>(tmem_lane, 1, hsel, GATE_COL, b.acc_free + 8, b.a_ready + 8, b.a_ready + 8, lane);
       }
       // ---- L0..L7 ----
       for (int l = 0; l < 8; ++l) {
 #ifdef ZEST_TC_TIMELINE
         const bool tl_on = p.tl && blockIdx.x == 0 && it == 3 && lane == 0;
         for (int part = 0; part < 2; ++part) {
-          uint32_t pk[32];
           long long t_ld = 0;
           wait_bar(b.acc_full + 8 * part, nfull[part]++ & 1, 310 + part);
           ptx::tc_fence_after();
           TL(warp, 100 * l + 10 * part + 0);
-          epilogue_compute<GATE32 ? 4 : 0>(tmem_lane, part, hsel, b.acc_free + 8 * part, lane, pk, &t_ld);
+          if (part == 0) epilogue_part<GATE32 ? 4 : 0>(tmem_lane, 0, hsel, ACT_COL, b.acc_free, b.a_ready, b.a_ready + 16, lane, &t_ld);
+          else epilogue_part<GATE32 ? 4 : 0>(tmem_lane, 1, hsel, ACT_COL, b.acc_free + 8, b.a_ready + 8, b.a_ready + 8, lane, &t_ld);
           if (tl_on) { p.tl[warp * 256 + tl_n[0]] = ((unsigned long long)(100 * l + 10 * part + 1) << 48) | (t_ld & 0xFFFFFFFFFFFFull); tl_n[0]++; }
-          TL(warp, 100 * l + 10 * part + 2);
-          epilogue_store(tmem_lane + ACT_COL + part * 64 + hsel * 32, pk, b.a_ready + 8 * part, lane);
           TL(warp, 100 * l + 10 * part + 3);
         }
 #else
-        epilogue_two_part<GATE32 ? 4 : 0>(tmem_lane, hsel, b, nfull, lane);
+        epilogue_two_part<GATE32 ? 4 : 0>(tmem_lane, hsel, b, nfull, lane, 310);
 #endif
       }
       // ---- FEAT + heads: the head accumulators (sigma + blend / scene flow / probs) are complete with
@@ -637,24 +659,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
           for (int k = 0; k < 2; ++k) head[10 + k] = 1.f / (1.f + __expf(-__uint_as_float(r[7 + k])));
         }
       }
-      {
-        uint32_t pk[32];
-        epilogue_compute<1>(tmem_lane, 0, hsel, b.acc_free, lane, pk);
-        epilogue_store(tmem_lane + ACT_COL + hsel * 32, pk, b.a_ready, lane);
-        wait_bar(b.acc_full + 8, nfull[1]++ & 1, 321);
-        ptx::tc_fence_after();
-        epilogue_compute<1>(tmem_lane, 1, hsel, b.acc_free + 8, lane, pk);
-        epilogue_store(tmem_lane + ACT_COL + 64 + hsel * 32, pk, b.a_ready + 8, lane);
-      }
+      epilogue_part<1>(tmem_lane, 0, hsel, ACT_COL, b.acc_free, b.a_ready, b.a_ready + 16, lane);
+      wait_bar(b.acc_full + 8, nfull[1]++ & 1, 321);
+      ptx::tc_fence_after();
+      epilogue_part<1>(tmem_lane, 1, hsel, ACT_COL, b.acc_free + 8, b.a_ready + 8, b.a_ready + 8, lane);
       // ---- VIEWS: relu -> v = activation columns [0, 128) ----
-      {
-        uint32_t pk[32];
-        wait_bar(b.acc_full, nfull[0]++ & 1, 340);
-        ptx::tc_fence_after();
-        epilogue_compute<2>(tmem_lane, 0, hsel, b.acc_free, lane, pk);
-        epilogue_store(tmem_lane + ACT_COL + hsel * 32, pk, b.a_ready, lane);
-        arrive_idle(b.acc_free + 8, b.a_ready + 8, lane);
-      }
+      wait_bar(b.acc_full, nfull[0]++ & 1, 340);
+      ptx::tc_fence_after();
+      epilogue_part<2>(tmem_lane, 0, hsel, ACT_COL, b.acc_free, b.a_ready, b.a_ready + 16, lane);
+      arrive_idle(b.acc_free + 8, b.a_ready + 8, lane);
       // ---- RGB (N = 16) -> raw ----
       wait_bar(b.acc_full, nfull[0]++ & 1, 350);
       ptx::tc_fence_after();
