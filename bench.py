@@ -316,6 +316,24 @@ def main():
         e2e = {"value": world * R * n_e2e / (float(t_e2e) * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": n_e2e, "api": "zest_nerf_b200.renderer.rendering, 8 slabs/frame, pinned host rays"}
 
+    # "next" row f1: the CUDA ray builder for one full frame (streaming writes: 28 B / sample + 12 B / ray), vs HBM peak
+    f1 = None
+    if rank == 0:
+        nf = torch.stack([sc.near_fars[0, 0], sc.near_fars[0, -1]]).view(1, 2, 2) if False else sc.near_fars
+        for _ in range(2):
+            ops.build_rays(H, W, sc.w2cs, sc.c2ws, sc.intrinsics, nf, S, pad=24, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            ops.build_rays(H, W, sc.w2cs, sc.c2ws, sc.intrinsics, nf, S, pad=24, device=dev)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        byts = R * S * 28 + R * 12
+        f1 = {"kernel": "build_rays_kernel (zest_build_rays)", "ms_per_frame": ms, "achieved_gbs": byts / ms / 1e6,
+              "peak_gbs": pk["hbm_gbs"], "frac": byts / ms / 1e6 / pk["hbm_gbs"], "bytes_per_frame": byts}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, sample = cpu_reference(args.config, 4096, 2)
@@ -329,7 +347,8 @@ def main():
                 "config": {"workload": args.config + ": " + c["desc"], "rays_per_gpu_per_step": R, "samples_per_ray": S,
                            "l2": "256 MiB buffer written between timed steps (L2 flush); per-step working set 3.6 GB > L2",
                            "parallelism": f"ray-sharded x{world}, one NCCL frame broadcast per step" if world > 1 else "1 GPU"},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+                "next_rows": {"f1_ray_builder": f1}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -137,10 +137,9 @@ class FrameRenderer:
         outs = []
         for a in range(r0, r1, max_rays):
             b = min(r1, a + max_rays)
-            lin = torch.arange(a, b, device=self.device)
-            ys, xs = (lin // W).float(), (lin % W).float()
-            pts, rdir, ndc, z = zrays.build_rays_val(H, W, w2cs, c2ws, intr, near_fars.to(self.device), self.n_samples,
-                                                     pad=self.pad, pixels=(ys, xs), src_hw=fr["hw"])
+            # CUDA ray builder: row-major grid slab [a, b), bit-identical to the reference's CPU ray builder
+            pts, rdir, ndc, z = ops.build_rays(H, W, w2cs, c2ws, intr, near_fars, self.n_samples, pad=self.pad, r0=a,
+                                               n_rays=b - a, src_hw=fr["hw"], device=self.device)
             outs.append(self.render_rays(pts, ndc, z, rdir, ref_frame_idx))
         if not outs:
             return {}

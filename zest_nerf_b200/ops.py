@@ -147,6 +147,44 @@ def gather_fwd(rays_pts, ndc, vol_cl, img_cl, cams, R, S, F, want_idx=False):
     return (feats, vox, pix) if want_idx else feats
 
 
+_tvals_cache = {}
+
+
+def build_rays(H_tgt, W_tgt, w2cs, c2ws, intrinsics, near_fars, n_samples=128, pad=24, r0=0, n_rays=None, pixels=None,
+               t_rand=None, src_hw=None, ref_idx=0, device=None):
+    """CUDA ray builder (zest_build_rays): same arguments / results as `rays.build_rays_val`, bit-identical to the
+    reference's CPU ray builder.  The target camera is the LAST view of w2cs / c2ws / intrinsics / near_fars."""
+    lib = _lib.load()
+    dev = torch.device(device if device is not None else "cuda")
+    S = int(n_samples)
+    key = (S, dev)
+    if key not in _tvals_cache:   # CPU linspace (the reference's formula), uploaded once
+        _tvals_cache[key] = torch.linspace(0.0, 1.0, steps=S).to(dev)
+    t_vals = _tvals_cache[key]
+    if pixels is not None:
+        ys, xs = (_f32c(t.to(dev), "pixels") for t in pixels)
+        R = ys.numel()
+    else:
+        ys = xs = None
+        R = H_tgt * W_tgt - r0 if n_rays is None else int(n_rays)
+    host = lambda t: t.detach().to("cpu", torch.float32).contiguous()
+    K_t, c2w_t = host(intrinsics[0, -1]), host(c2ws[0, -1])
+    w2c_r, K_r = host(w2cs[0, ref_idx]), host(intrinsics[0, ref_idx])
+    nf = host(near_fars[0])
+    sh, sw = (H_tgt, W_tgt) if src_hw is None else src_hw
+    pts = torch.empty((1, R, S, 3), device=dev, dtype=torch.float32)
+    ndc = torch.empty((1, R, S, 3), device=dev, dtype=torch.float32)
+    rdir = torch.empty((1, R, 3), device=dev, dtype=torch.float32)
+    z = torch.empty((1, R, S), device=dev, dtype=torch.float32)
+    tr = _f32c(t_rand.to(dev), "t_rand") if t_rand is not None else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.zest_build_rays(_ptr(ys), _ptr(xs), int(r0), int(W_tgt), C.c_void_p(K_t.data_ptr()), C.c_void_p(c2w_t.data_ptr()),
+                                       C.c_void_p(w2c_r.data_ptr()), C.c_void_p(K_r.data_ptr()), float(nf[-1, 0]), float(nf[-1, 1]),
+                                       float(nf[ref_idx, 0]), float(nf[ref_idx, 1]), int(sw), int(sh), int(pad), _ptr(t_vals), _ptr(tr),
+                                       R, S, _ptr(pts), _ptr(rdir), _ptr(ndc), _ptr(z), _stream()), "zest_build_rays")
+    return pts, rdir, ndc, z
+
+
 def dirfeat(rays_dir, cams):
     """cos_angle [R], dirs [R,3] for the reference view (row 0 of the cam table)."""
     rd = _f32c(rays_dir.reshape(-1, 3), "rays_dir")
