@@ -139,18 +139,17 @@ int zest_mlp_fwd_tc_x(const zest_net* net, const float* x, int ldx, int64_t M, f
 
 /* ---- ray builder ("next" row f1) ---------------------------------------------------------------
  * Replaces utils.get_rays_mvs (utils.py:133-230) + build_rays_base (utils.py:290-394: sample depths,
- * world points) + get_ndc_coordinate (utils.py:232-288) for one slab of target pixels.  The camera
- * matrices are HOST pointers (row-major: K 3x3, c2w / w2c 4x4); everything else is device memory.
+ * world points) + get_ndc_coordinate (utils.py:232-288) for one slab of target pixels.
+ * cam: DEVICE table of 54 floats (row-major): K_tgt 3x3 | c2w_tgt 4x4 | w2c_ref 4x4 | K_ref 3x3 |
+ * near_tgt far_tgt near_ref far_ref - stream-ordered with whatever produced the pose, no host sync.
  * ys/xs: R target pixel coordinates (fp32) or both NULL = the row-major grid slab [r0, r0 + R) of a
  * W_tgt wide image.  t_vals: [S] = torch.linspace(0, 1, S).  t_rand: [R, S] stratified jitter or
  * NULL.  W_src/H_src: size of the SOURCE views (NDC normalisation, utils.py:318).  Outputs:
  * rays_pts [R,S,3], rays_dir [R,3], rays_ndc [R,S,3], depth [R,S] - bit-identical to the
  * reference's CPU path (separately rounded ops, fma-chain K = 3 matmuls, reciprocal*pad quirk). */
-int zest_build_rays(const float* ys, const float* xs, int64_t r0, int W_tgt, const float* K_tgt,
-                    const float* c2w_tgt, const float* w2c_ref, const float* K_ref, float near_t,
-                    float far_t, float near_r, float far_r, int W_src, int H_src, int pad,
-                    const float* t_vals, const float* t_rand, int64_t R, int S, float* rays_pts,
-                    float* rays_dir, float* rays_ndc, float* depth, void* stream);
+int zest_build_rays(const float* ys, const float* xs, int64_t r0, int W_tgt, const float* cam,
+                    int W_src, int H_src, int pad, const float* t_vals, const float* t_rand, int64_t R,
+                    int S, float* rays_pts, float* rays_dir, float* rays_ndc, float* depth, void* stream);
 
 /* ---- alpha compositing (warp per ray) ---------------------------------------------------- */
 /* raw [R*S, ld_raw] (rgb_raw 3, sigma_raw 1, ...), z [R,S], cos_angle [R], noise [R,S] or NULL

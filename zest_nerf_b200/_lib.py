@@ -43,7 +43,7 @@ SIGNATURES = {
     "zest_composite_static_bwd": (_i, [_p, _i, _p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
     "zest_composite_blend_fwd": (_i, [_p, _i, _p, _i, _p, _p, _p, _l, _i, _f, _p, _p, _p, _p, _p, _p, _p]),
     "zest_composite_blend_bwd": (_i, [_p, _i, _p, _i, _p, _p, _p, _l, _i, _p, _p, _p, _p, _p, _p, _i, _p, _i, _p]),
-    "zest_build_rays": (_i, [_p, _p, _l, _i, _p, _p, _p, _p, _f, _f, _f, _f, _i, _i, _i, _p, _p, _l, _i, _p, _p, _p, _p, _p]),
+    "zest_build_rays": (_i, [_p, _p, _l, _i, _p, _i, _i, _i, _p, _p, _l, _i, _p, _p, _p, _p, _p]),
     "zest_tc_selftest": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "zest_tc_set_timeline": (_i, [_p]),
     "zest_tc_rate_probe": (_i, [_i, _i, _i, _i, _p, _p]),

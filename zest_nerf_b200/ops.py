@@ -150,8 +150,15 @@ def gather_fwd(rays_pts, ndc, vol_cl, img_cl, cams, R, S, F, want_idx=False):
 _tvals_cache = {}
 
 
+def ray_cam_table(w2cs, c2ws, intrinsics, near_fars, ref_idx=0, device="cuda"):
+    """The 54-float device table zest_build_rays reads: K_tgt | c2w_tgt | w2c_ref | K_ref | near/far tgt | near/far ref."""
+    f = lambda t: t.detach().to(device, torch.float32).reshape(-1)
+    return torch.cat([f(intrinsics[0, -1]), f(c2ws[0, -1]), f(w2cs[0, ref_idx]), f(intrinsics[0, ref_idx]),
+                      f(near_fars[0, -1]), f(near_fars[0, ref_idx])]).contiguous()
+
+
 def build_rays(H_tgt, W_tgt, w2cs, c2ws, intrinsics, near_fars, n_samples=128, pad=24, r0=0, n_rays=None, pixels=None,
-               t_rand=None, src_hw=None, ref_idx=0, device=None):
+               t_rand=None, src_hw=None, ref_idx=0, device=None, cam=None, out=None):
     """CUDA ray builder (zest_build_rays): same arguments / results as `rays.build_rays_val`, bit-identical to the
     reference's CPU ray builder.  The target camera is the LAST view of w2cs / c2ws / intrinsics / near_fars."""
     lib = _lib.load()
@@ -167,21 +174,20 @@ def build_rays(H_tgt, W_tgt, w2cs, c2ws, intrinsics, near_fars, n_samples=128, p
     else:
         ys = xs = None
         R = H_tgt * W_tgt - r0 if n_rays is None else int(n_rays)
-    host = lambda t: t.detach().to("cpu", torch.float32).contiguous()
-    K_t, c2w_t = host(intrinsics[0, -1]), host(c2ws[0, -1])
-    w2c_r, K_r = host(w2cs[0, ref_idx]), host(intrinsics[0, ref_idx])
-    nf = host(near_fars[0])
+    if cam is None:
+        cam = ray_cam_table(w2cs, c2ws, intrinsics, near_fars, ref_idx, dev)   # 54 floats, no host sync
     sh, sw = (H_tgt, W_tgt) if src_hw is None else src_hw
-    pts = torch.empty((1, R, S, 3), device=dev, dtype=torch.float32)
-    ndc = torch.empty((1, R, S, 3), device=dev, dtype=torch.float32)
-    rdir = torch.empty((1, R, 3), device=dev, dtype=torch.float32)
-    z = torch.empty((1, R, S), device=dev, dtype=torch.float32)
+    if out is not None:     # caller-owned buffers (pts [1,R,S,3], dir [1,R,3], ndc [1,R,S,3], z [1,R,S]) are reused
+        pts, rdir, ndc, z = out
+    else:
+        pts = torch.empty((1, R, S, 3), device=dev, dtype=torch.float32)
+        ndc = torch.empty((1, R, S, 3), device=dev, dtype=torch.float32)
+        rdir = torch.empty((1, R, 3), device=dev, dtype=torch.float32)
+        z = torch.empty((1, R, S), device=dev, dtype=torch.float32)
     tr = _f32c(t_rand.to(dev), "t_rand") if t_rand is not None else None
     with torch.cuda.device(dev):
-        _lib.check(lib.zest_build_rays(_ptr(ys), _ptr(xs), int(r0), int(W_tgt), C.c_void_p(K_t.data_ptr()), C.c_void_p(c2w_t.data_ptr()),
-                                       C.c_void_p(w2c_r.data_ptr()), C.c_void_p(K_r.data_ptr()), float(nf[-1, 0]), float(nf[-1, 1]),
-                                       float(nf[ref_idx, 0]), float(nf[ref_idx, 1]), int(sw), int(sh), int(pad), _ptr(t_vals), _ptr(tr),
-                                       R, S, _ptr(pts), _ptr(rdir), _ptr(ndc), _ptr(z), _stream()), "zest_build_rays")
+        _lib.check(lib.zest_build_rays(_ptr(ys), _ptr(xs), int(r0), int(W_tgt), _ptr(cam), int(sw), int(sh), int(pad), _ptr(t_vals),
+                                       _ptr(tr), R, S, _ptr(pts), _ptr(rdir), _ptr(ndc), _ptr(z), _stream()), "zest_build_rays")
     return pts, rdir, ndc, z
 
 
