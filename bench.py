@@ -83,16 +83,22 @@ class ClockSampler(threading.Thread):
             pass
 
     def stop(self, t0=None, t1=None):
+        if self.proc and not any(t0 is None or ts >= t0 for ts, _ in self.rows):
+            time.sleep(0.25)      # give the first poll a chance to land
         if self.proc:
             self.proc.terminate()
+        # a region shorter than nvidia-smi's start-up has no sample inside it: then the first sample after it counts
+        late_ok = t0 is not None and not any(t0 <= ts <= t1 + 0.05 for ts, _ in self.rows)
+        if late_ok and not self.rows:
+            time.sleep(0.3)
         sm, pw, reasons, mx = [], [], set(), 0
-        for ts, r in self.rows:
+        for ts, r in self.rows[:1] if late_ok else self.rows:
             try:
                 clk, cmax, p = float(r[1]), float(r[2]), float(r[3])
             except Exception:
                 continue
             mx = max(mx, cmax)
-            if t0 is not None and not (t0 <= ts <= t1 + 0.05):
+            if t0 is not None and not (t0 <= ts <= t1 + 0.05) and not (late_ok and ts > t1):
                 continue
             sm.append(clk); pw.append(p)
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
