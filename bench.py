@@ -340,10 +340,10 @@ def main():
             ops.build_rays(H, W, sc.w2cs, sc.c2ws, sc.intrinsics, sc.near_fars, S, pad=24, device=dev, cam=cam, out=bufs)
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 5
+        f1_ms = e0.elapsed_time(e1) / 5
         byts = R * S * 28 + R * 12
-        f1 = {"kernel": "build_rays_kernel (zest_build_rays)", "ms_per_frame": ms, "achieved_gbs": byts / ms / 1e6,
-              "peak_gbs": pk["hbm_gbs"], "frac": byts / ms / 1e6 / pk["hbm_gbs"], "bytes_per_frame": byts}
+        f1 = {"kernel": "build_rays_kernel (zest_build_rays)", "ms_per_frame": f1_ms, "achieved_gbs": byts / f1_ms / 1e6,
+              "peak_gbs": pk["hbm_gbs"], "frac": byts / f1_ms / 1e6 / pk["hbm_gbs"], "bytes_per_frame": byts}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -358,7 +358,7 @@ def main():
                 "config": {"workload": args.config + ": " + c["desc"], "rays_per_gpu_per_step": R, "samples_per_ray": S,
                            "l2": "256 MiB buffer written between timed steps (L2 flush); per-step working set 3.6 GB > L2",
                            "parallelism": f"ray-sharded x{world}, one NCCL frame broadcast per step" if world > 1 else "1 GPU"},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+                "steps_ms": [round(x, 3) for x in ms], "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
                 "next_rows": {"f1_ray_builder": f1}}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -25,8 +25,8 @@
 // Shared memory therefore only holds the small per-tile inputs (PE, dirPE, feats: SS-form MMAs)
 // and a deep weight ring, and the MMA operand traffic out of shared memory is halved.
 //
-// Warp roles (384 threads): warps 0-7 epilogue (TMEM lane quarter = warp % 4, column half = warp / 4),
-// warps 10-11 loaders (two sample rows per thread: they gather the NEXT tile's features from the encoding
+// Warp roles (384 or 448 threads): warps 0-7 epilogue (TMEM lane quarter = warp % 4, column half = warp / 4),
+// warps 10-11 (or 10-13 when V > 6) loaders (two / one sample rows per thread: they gather the NEXT tile's features from the encoding
 // volume / source views, encode PE and stage everything as bf16 operands while the current tile is in
 // the tensor pipe), warp 8 = weight producer (cp.async.bulk / UBLKCP, weights pre-packed on the
 // host side of the ABI in the exact smem image, consumption order), warp 9 = MMA issuer + TMEM
@@ -57,8 +57,8 @@ constexpr int kStages = 4;
 constexpr int kChunkBytes = kTile * 16;  // one 8-column k-chunk of a 128-row smem operand tile
 constexpr int kMaxPlan = 64;
 constexpr int kEpiWarps = 8;
-constexpr int kLoadWarps = 2;             // stage the next tile's inputs (gather + PE), two rows per thread
-constexpr int kThreads = 32 * (kEpiWarps + 2 + kLoadWarps);
+// loader warps stage the next tile's inputs (gather + PE): 2 (two rows per thread, 168-register budget for the
+// epilogue) or 4 (one row per thread, 128 registers: needed when many source views make the gather the long pole)
 constexpr int kMaxViews = 14;             // 8 + 4 V <= 64 feature columns
 #define ACC_COL_OF(part) ((uint32_t)(part) * 128u)
 constexpr uint32_t GATE_COL = 256, HEAD_COL = 256, HEAD2_COL = 272, ACT_COL = 384;
@@ -300,13 +300,14 @@ __device__ __forceinline__ void mma_skip(MmaCtx& c) {
   ++c.n_issued;
 }
 
-template <int C, bool GATE32>  // C = 3 (static: xyz) or 4 (dynamic: xyz + t); GATE32: fp32 gate multiply
-__global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
+template <int C, bool GATE32, int kLoadWarps>  // C = 3 (static: xyz) or 4 (dynamic: xyz + t); GATE32: fp32 gate multiply
+__global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_bars[2 * kStages + 10];
   __shared__ float s_cams[kMaxViews * 24];
   __shared__ uint32_t s_tmem;
 
+  constexpr int kThreads = 32 * (kEpiWarps + 2 + kLoadWarps), kRowsPerLoader = kTile / (32 * kLoadWarps);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // smem: S = [PE (Ppad/8 chunks) | dirPE x 2 (4 + 4) | ones (2) | feats (Fpad/8)] then the weight ring.
   // dirPE is double buffered by tile parity: it is read at the very end of a tile (VIEWS), after the
@@ -488,8 +489,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     for (int64_t it = 0; it < my_tiles; ++it) {
       if (it > 0) wait_bar(feats_free, (uint32_t)((it - 1) & 1), 400);
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const int row = row0 + 64 * h;
+      for (int h = 0; h < kRowsPerLoader; ++h) {
+        const int row = row0 + 32 * kLoadWarps * h;
         const int64_t m = (blockIdx.x + it * gridDim.x) * kTile + row;
         const bool valid = m < p.M;
         // ---- gathered features: fused trilinear volume sample + per-view bilinear RGB + mask (gather_core.cuh),
@@ -547,8 +548,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         }
       }
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const int row = row0 + 64 * h;
+      for (int h = 0; h < kRowsPerLoader; ++h) {
+        const int row = row0 + 32 * kLoadWarps * h;
         const int64_t m = (blockIdx.x + it * gridDim.x) * kTile + row;
         const bool valid = m < p.M;
         // ---- direction PE (this tile parity's buffer: its last reader, VIEWS two tiles ago, retired long ago) ----
@@ -571,8 +572,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       }
       if (it > 0) wait_bar(pe_free, (uint32_t)((it - 1) & 1), 401);
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const int row = row0 + 64 * h;
+      for (int h = 0; h < kRowsPerLoader; ++h) {
+        const int row = row0 + 32 * kLoadWarps * h;
         const int64_t m = (blockIdx.x + it * gridDim.x) * kTile + row;
         const bool valid = m < p.M;
         // ---- point PE ----
@@ -933,13 +934,19 @@ static int tc_launch(const zest_net* net, TcParams& p, cudaStream_t st) {
   p.n_tiles = (p.M + kTile - 1) / kTile;
   if (p.M == 0) return ZEST_OK;
   const int grid = (int)(p.n_tiles < num_sms() ? p.n_tiles : num_sms());
-#define ZEST_TC_GO(CC, G32)                                                                                              \
-  do {                                                                                                                   \
-    ZEST_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<CC, G32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ph->smem_bytes)); \
-    mlp_tc_kernel<CC, G32><<<grid, kThreads, ph->smem_bytes, st>>>(p);                                                  \
+#define ZEST_TC_GO(CC, G32, LW)                                                                                              \
+  do {                                                                                                                       \
+    ZEST_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<CC, G32, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ph->smem_bytes)); \
+    mlp_tc_kernel<CC, G32, LW><<<grid, 32 * (kEpiWarps + 2 + LW), ph->smem_bytes, st>>>(p);                                  \
   } while (0)
-  if (ph->C == 3) { if (ph->gate_fp32) ZEST_TC_GO(3, true); else ZEST_TC_GO(3, false); }
-  else { if (ph->gate_fp32) ZEST_TC_GO(4, true); else ZEST_TC_GO(4, false); }
+  const bool wide = p.vol && p.V > 6;   // many source views: the in-kernel gather needs four loader warps
+  if (ph->C == 3) {
+    if (ph->gate_fp32) { if (wide) ZEST_TC_GO(3, true, 4); else ZEST_TC_GO(3, true, 2); }
+    else { if (wide) ZEST_TC_GO(3, false, 4); else ZEST_TC_GO(3, false, 2); }
+  } else {
+    if (ph->gate_fp32) { if (wide) ZEST_TC_GO(4, true, 4); else ZEST_TC_GO(4, true, 2); }
+    else { if (wide) ZEST_TC_GO(4, false, 4); else ZEST_TC_GO(4, false, 2); }
+  }
 #undef ZEST_TC_GO
   ZEST_LAUNCH_CHECK();
   return ZEST_OK;
