@@ -63,6 +63,17 @@ constexpr int kMaxViews = 14;             // 8 + 4 V <= 64 feature columns
 #define ACC_COL_OF(part) ((uint32_t)(part) * 128u)
 constexpr uint32_t GATE_COL = 256, HEAD_COL = 256, HEAD2_COL = 272, ACT_COL = 384;
 
+// Biases of the 256-wide ops: folded into the MMA as one extra K = 16 step per accumulator group (default), or
+// (-DZEST_TC_BIAS_IN_EPILOGUE) added by the epilogue in fp32 (packed FADD2 against a bias table in shared memory).
+// Same-box A/B on cfg2: the epilogue variant saves 6 % of the issued UMMAs but is 2.4 % slower (the epilogue sits on
+// the critical path between layers; the tensor pipe has the slack).
+#ifdef ZEST_TC_BIAS_IN_EPILOGUE
+constexpr bool kBiasInMma = false;
+#else
+constexpr bool kBiasInMma = true;
+#endif
+constexpr int kBiasOps = 11;   // GATE, L0..L7, FEAT, VIEWS: 256 fp32 each in the shared-memory bias table
+
 struct TcStage {   // one ring slot's worth of weights (bytes = 0: an empty stage that only keeps the ring aligned)
   uint32_t src_off;  // byte offset in the packed blob
   uint32_t bytes;
@@ -83,6 +94,7 @@ struct TcPlanHost {
 struct TcParams {
   TcStage plan[kMaxPlan]; int n_stages;  // by value: lives in the constant bank -> uniform loads in the producer loop
   const uint8_t* blob;
+  const float* bias;   // [kBiasOps][256] fp32 (epilogue-side biases)
   // inputs (fused mode) or x (x mode)
   const float* ndc; int ndc_ld; int has_t; float t;
   const float* feats; int ldf;
@@ -161,26 +173,34 @@ struct Bars {
 // [64 + hsel*32, +32), so that the eight warps together finish columns 0..63 first: those are K columns 0..63 of the
 // next layer's input and get their own a_ready barrier (the next layer's first four UMMAs start half an epilogue earlier).
 template <int MODE>
-__device__ __forceinline__ void epi_math(const uint32_t (&acc)[32], const uint32_t (&g)[16], uint32_t (&packed)[16]) {
+__device__ __forceinline__ uint32_t epi_pair(float v0, float v1, float b0, float b1, uint32_t g01) {
+  if (!kBiasInMma) ptx::add_f32x2(v0, v1, b0, b1);
+  if (MODE == 4) ptx::mul_f32x2(v0, v1, ptx::bf16_lo(g01), ptx::bf16_hi(g01));
+  uint32_t pk = ptx::pack_bf16(v0, v1);
+  if (MODE == 0) pk = ptx::mul_relu_bf16x2(pk, g01);
+  if (MODE == 4 || MODE == 2) pk = ptx::relu_bf16x2(pk);
+  return pk;
+}
+
+// 32 accumulator columns -> 16 packed pairs.  bias_s: shared-memory address of this run's 32 fp32 biases (the same
+// address in every lane: broadcast reads).
+template <int MODE>
+__device__ __forceinline__ void epi_math(const uint32_t (&acc)[32], const uint32_t (&g)[16], uint32_t (&packed)[16], uint32_t bias_s) {
 #pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    float v0 = __uint_as_float(acc[j]), v1 = __uint_as_float(acc[j + 1]);
-    if (MODE == 4) {
-      const uint32_t g01 = g[j / 2];
-      ptx::mul_f32x2(v0, v1, ptx::bf16_lo(g01), ptx::bf16_hi(g01));
-    }
-    uint32_t pk = ptx::pack_bf16(v0, v1);
-    if (MODE == 0) pk = ptx::mul_relu_bf16x2(pk, g[j / 2]);
-    if (MODE == 4 || MODE == 2) pk = ptx::relu_bf16x2(pk);
-    packed[j / 2] = pk;
+  for (int j = 0; j < 32; j += 4) {
+    uint4 bq = make_uint4(0u, 0u, 0u, 0u);
+    if (!kBiasInMma) bq = ptx::ld_smem_v4(bias_s + j * 4);
+    packed[j / 2] = epi_pair<MODE>(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(bq.x), __uint_as_float(bq.y), g[j / 2]);
+    packed[j / 2 + 1] = epi_pair<MODE>(__uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]), __uint_as_float(bq.z), __uint_as_float(bq.w), g[j / 2 + 1]);
   }
 }
 
 // out_base: TMEM column base of the destination (ACT_COL or GATE_COL).  bar_free: arrive once the accumulator is in
 // registers.  bar_rdy0 / bar_rdy1: arrive after sub-half 0 / 1 has landed (pass the same barrier twice -> arrive once, at the end).
 template <int MODE>
-__device__ __forceinline__ void epilogue_part(uint32_t tmem_lane, int part, int hsel, uint32_t out_base, uint32_t bar_free,
-                                              uint32_t bar_rdy0, uint32_t bar_rdy1, int lane, long long* t_ld = nullptr) {
+__device__ __forceinline__ void epilogue_part(uint32_t tmem_lane, int part, int hsel, uint32_t out_base, uint32_t bias_op,
+                                              uint32_t bar_free, uint32_t bar_rdy0, uint32_t bar_rdy1, int lane, long long* t_ld = nullptr) {
+  const uint32_t bias_s = bias_op + (uint32_t)(part * 128 + hsel * 32) * 4u;   // this thread's first run of 32 columns
   const uint32_t acc_t = tmem_lane + ACC_COL_OF(part) + hsel * 32;
   const uint32_t gate_t = tmem_lane + GATE_COL + part * 64 + hsel * 16;
   const uint32_t out_t = tmem_lane + out_base + part * 64 + hsel * 16;
@@ -195,7 +215,7 @@ __device__ __forceinline__ void epilogue_part(uint32_t tmem_lane, int part, int 
   ptx::tc_fence_before();
   __syncwarp();
   if (lane == 0) ptx::mbar_arrive(bar_free);
-  epi_math<MODE>(acc[0], g[0], pk);
+  epi_math<MODE>(acc[0], g[0], pk, bias_s);
   ptx::tmem_st16(out_t, pk);
   if (bar_rdy0 != bar_rdy1) {
     ptx::tc_wait_st();
@@ -203,7 +223,7 @@ __device__ __forceinline__ void epilogue_part(uint32_t tmem_lane, int part, int 
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(bar_rdy0);
   }
-  epi_math<MODE>(acc[1], g[1], pk);
+  epi_math<MODE>(acc[1], g[1], pk, bias_s + 64 * 4);
   ptx::tmem_st16(out_t + 32, pk);
   ptx::tc_wait_st();
   ptx::tc_fence_before();
@@ -219,13 +239,13 @@ __device__ __forceinline__ void arrive_idle(uint32_t bar_free, uint32_t bar_read
 // two-part hidden op (L0..L7, FEAT): part p's outputs are K half p of the next layer's input, stored in place.
 // a_ready: [0] = K columns 0..63, [2] = 64..127 (part 0's two sub-halves), [1] = 128..255 (part 1).
 template <int MODE>
-__device__ __forceinline__ void epilogue_two_part(uint32_t tmem_lane, int hsel, const Bars& b, uint32_t (&nfull)[2], int lane, int tag) {
+__device__ __forceinline__ void epilogue_two_part(uint32_t tmem_lane, int hsel, uint32_t bias_op, const Bars& b, uint32_t (&nfull)[2], int lane, int tag) {
   wait_bar(b.acc_full, nfull[0]++ & 1, tag);
   ptx::tc_fence_after();
-  epilogue_part<MODE>(tmem_lane, 0, hsel, ACT_COL, b.acc_free, b.a_ready, b.a_ready + 16, lane);
+  epilogue_part<MODE>(tmem_lane, 0, hsel, ACT_COL, bias_op, b.acc_free, b.a_ready, b.a_ready + 16, lane);
   wait_bar(b.acc_full + 8, nfull[1]++ & 1, tag + 1);
   ptx::tc_fence_after();
-  epilogue_part<MODE>(tmem_lane, 1, hsel, ACT_COL, b.acc_free + 8, b.a_ready + 8, b.a_ready + 8, lane);
+  epilogue_part<MODE>(tmem_lane, 1, hsel, ACT_COL, bias_op, b.acc_free + 8, b.a_ready + 8, b.a_ready + 8, lane);
 }
 
 // ---- MMA issue helpers (warp-convergent; every operand warp-uniform; one elected lane issues) ------
@@ -314,7 +334,8 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
   // next tile's inputs have been staged; PE (last read by L5) and feats (GATE) are not.
   const uint32_t s_base = ptx::smem_u32(smem_raw);
   const int dir_chunk = p.Ppad / 8, ones_chunk = dir_chunk + 8, feat_chunk = ones_chunk + 2;
-  const uint32_t ring = s_base + (feat_chunk + p.Fpad / 8) * kChunkBytes;
+  const uint32_t bias_s0 = s_base + (feat_chunk + p.Fpad / 8) * kChunkBytes;   // [kBiasOps][256] fp32
+  const uint32_t ring = bias_s0 + (kBiasInMma ? 0 : kBiasOps * 1024);
   const uint32_t bars = ptx::smem_u32(s_bars);
   Bars b;
   b.full = bars; b.empty = bars + 8 * kStages; b.acc_full = bars + 16 * kStages;
@@ -333,6 +354,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
     ptx::mbar_init(in_ready, kLoadWarps); ptx::mbar_init(feats_free, 1); ptx::mbar_init(pe_free, 1);
     ptx::fence_mbar_init();
   }
+  if (!kBiasInMma) for (int i = tid; i < kBiasOps * 256; i += kThreads) ptx::st_smem_u32(bias_s0 + i * 4, __float_as_uint(__ldg(p.bias + i)));
   if (tid < kTile) {  // the constant "ones" A chunk pair: columns 0, 1 = 1.0 (bias hi, lo), the rest 0
     ptx::st_smem_v4(s_base + ones_chunk * kChunkBytes + tid * 16, 0x3F803F80u, 0u, 0u, 0u);
     ptx::st_smem_v4(s_base + (ones_chunk + 1) * kChunkBytes + tid * 16, 0u, 0u, 0u, 0u);
@@ -395,16 +417,16 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
       // ---- revolution 0: GATE (feats, SS) | L0 (PE, SS) ----
       wait_bar(in_ready, (uint32_t)(it & 1), 210);   // the loader warps have staged this tile's operands
       c.next_op(); c.wait(31u);
-      mma_stage<128, false, 0>(c, feat_lo, nk_f, acc0, true, true, 0);
-      mma_stage<128, false, 1>(c, feat_lo, nk_f, acc1, true, true, 1);
+      mma_stage<128, false, 0>(c, feat_lo, nk_f, acc0, true, kBiasInMma, 0);
+      mma_stage<128, false, 1>(c, feat_lo, nk_f, acc1, true, kBiasInMma, 1);
       if (ptx::elect_one()) ptx::mma_commit(feats_free);   // feats operand may be overwritten once GATE has retired
       __syncwarp();
       c.next_op();
       if (!ov) c.wait(31u);
       c.wait(4u | 1u | 16u);   // every barrier of part X must be observed before the commit that lets X complete again
-      mma_stage<128, false, 2>(c, pe_lo, nk_p, acc0, true, true, 0);
+      mma_stage<128, false, 2>(c, pe_lo, nk_p, acc0, true, kBiasInMma, 0);
       c.wait(8u | 2u);
-      mma_stage<128, false, 3>(c, pe_lo, nk_p, acc1, true, true, 1);
+      mma_stage<128, false, 3>(c, pe_lo, nk_p, acc1, true, kBiasInMma, 1);
       c.end_revolution();
       // ---- L1..L7: (p0, K lo) (p1, K lo) (p0, K hi) (p1, K hi); L5 = [pe | h4] starts with the PE blocks (smem) ----
       for (int l = 1; l < 8; ++l) {
@@ -422,8 +444,8 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
           mma_stage<128, true, 3>(c, act, 8, acc1, false, false, -1);
           c.end_revolution();
           c.wait(2u);
-          mma_stage<128, true, 0>(c, act + 64, 8, acc0, false, true, 0);
-          mma_stage<128, true, 1>(c, act + 64, 8, acc1, false, true, 1);
+          mma_stage<128, true, 0>(c, act + 64, 8, acc0, false, kBiasInMma, 0);
+          mma_stage<128, true, 1>(c, act + 64, 8, acc1, false, kBiasInMma, 1);
           mma_skip<2>(c);
           mma_skip<3>(c);
           c.end_revolution();
@@ -441,9 +463,9 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
           TL(9, 100 * l + 53);
           c.wait(2u);
           TL(9, 100 * l + 54);
-          mma_stage<128, true, 2>(c, act + 64, 8, acc0, false, true, 0);
+          mma_stage<128, true, 2>(c, act + 64, 8, acc0, false, kBiasInMma, 0);
           TL(9, 100 * l + 55);
-          mma_stage<128, true, 3>(c, act + 64, 8, acc1, false, true, 1);
+          mma_stage<128, true, 3>(c, act + 64, 8, acc1, false, kBiasInMma, 1);
           TL(9, 100 * l + 56);
           c.end_revolution();
         }
@@ -457,9 +479,9 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
       mma_stage<128, true, 1>(c, act, 8, acc1, true, false, -1);
       c.wait(2u);
       mma_stage<16, true, 2>(c, act, 16, tmem + HEAD_COL, true, true, -1);
-      mma_stage<128, true, 3>(c, act + 64, 8, acc0, false, true, 0);
+      mma_stage<128, true, 3>(c, act + 64, 8, acc0, false, kBiasInMma, 0);
       c.end_revolution();
-      mma_stage<128, true, 0>(c, act + 64, 8, acc1, false, true, 1);
+      mma_stage<128, true, 0>(c, act + 64, 8, acc1, false, kBiasInMma, 1);
       // ---- VIEWS: [feature (TMEM) | dirPE (smem)] -> acc0 (N = 128, single part); RGB (N = 16) from v ----
       c.next_op();
       if (!ov) c.wait(31u);
@@ -467,7 +489,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
       mma_stage<128, true, 1>(c, act, 8, acc0, true, false, -1, 16u);
       c.wait(2u | 8u);
       mma_stage<128, true, 2>(c, act + 64, 8, acc0, false, false, -1);
-      mma_stage<128, false, 3>(c, dir_lo[it & 1], 2, acc0, false, true, 0);
+      mma_stage<128, false, 3>(c, dir_lo[it & 1], 2, acc0, false, kBiasInMma, 0);
       c.end_revolution();
       c.next_op(); c.wait(31u);
       mma_stage<16, true, 0>(c, act, 8, tmem + HEAD2_COL, true, true, 0);
@@ -619,8 +641,8 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
       for (int part = 0; part < 2; ++part) {
         wait_bar(b.acc_full + 8 * part, nfull[part]++ & 1, 300 + part);
         ptx::tc_fence_after();
-        if (part == 0) epilogue_part<3>(tmem_lane, 0, hsel, GATE_COL, b.acc_free, b.a_ready, b.a_ready + 16, lane);
-        else epilogue_part<3>(tmem_lane, 1, hsel, GATE_COL, b.acc_free + 8, b.a_ready + 8, b.a_ready + 8, lane);
+        if (part == 0) epilogue_part<3>(tmem_lane, 0, hsel, GATE_COL, bias_s0, b.acc_free, b.a_ready, b.a_ready + 16, lane);
+        else epilogue_part<3>(tmem_lane, 1, hsel, GATE_COL, bias_s0, b.acc_free + 8, b.a_ready + 8, b.a_ready + 8, lane);
       }
       // ---- L0..L7 ----
       for (int l = 0; l < 8; ++l) {
@@ -631,13 +653,13 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
           wait_bar(b.acc_full + 8 * part, nfull[part]++ & 1, 310 + part);
           ptx::tc_fence_after();
           TL(warp, 100 * l + 10 * part + 0);
-          if (part == 0) epilogue_part<GATE32 ? 4 : 0>(tmem_lane, 0, hsel, ACT_COL, b.acc_free, b.a_ready, b.a_ready + 16, lane, &t_ld);
-          else epilogue_part<GATE32 ? 4 : 0>(tmem_lane, 1, hsel, ACT_COL, b.acc_free + 8, b.a_ready + 8, b.a_ready + 8, lane, &t_ld);
+          if (part == 0) epilogue_part<GATE32 ? 4 : 0>(tmem_lane, 0, hsel, ACT_COL, bias_s0 + (1 + l) * 1024, b.acc_free, b.a_ready, b.a_ready + 16, lane, &t_ld);
+          else epilogue_part<GATE32 ? 4 : 0>(tmem_lane, 1, hsel, ACT_COL, bias_s0 + (1 + l) * 1024, b.acc_free + 8, b.a_ready + 8, b.a_ready + 8, lane, &t_ld);
           if (tl_on) { p.tl[warp * 256 + tl_n[0]] = ((unsigned long long)(100 * l + 10 * part + 1) << 48) | (t_ld & 0xFFFFFFFFFFFFull); tl_n[0]++; }
           TL(warp, 100 * l + 10 * part + 3);
         }
 #else
-        epilogue_two_part<GATE32 ? 4 : 0>(tmem_lane, hsel, b, nfull, lane, 310);
+        epilogue_two_part<GATE32 ? 4 : 0>(tmem_lane, hsel, bias_s0 + (1 + l) * 1024, b, nfull, lane, 310);
 #endif
       }
       // ---- FEAT + heads: the head accumulators (sigma + blend / scene flow / probs) are complete with
@@ -660,14 +682,14 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
           for (int k = 0; k < 2; ++k) head[10 + k] = 1.f / (1.f + __expf(-__uint_as_float(r[7 + k])));
         }
       }
-      epilogue_part<1>(tmem_lane, 0, hsel, ACT_COL, b.acc_free, b.a_ready, b.a_ready + 16, lane);
+      epilogue_part<1>(tmem_lane, 0, hsel, ACT_COL, bias_s0 + 9 * 1024, b.acc_free, b.a_ready, b.a_ready + 16, lane);
       wait_bar(b.acc_full + 8, nfull[1]++ & 1, 321);
       ptx::tc_fence_after();
-      epilogue_part<1>(tmem_lane, 1, hsel, ACT_COL, b.acc_free + 8, b.a_ready + 8, b.a_ready + 8, lane);
+      epilogue_part<1>(tmem_lane, 1, hsel, ACT_COL, bias_s0 + 9 * 1024, b.acc_free + 8, b.a_ready + 8, b.a_ready + 8, lane);
       // ---- VIEWS: relu -> v = activation columns [0, 128) ----
       wait_bar(b.acc_full, nfull[0]++ & 1, 340);
       ptx::tc_fence_after();
-      epilogue_part<2>(tmem_lane, 0, hsel, ACT_COL, b.acc_free, b.a_ready, b.a_ready + 16, lane);
+      epilogue_part<2>(tmem_lane, 0, hsel, ACT_COL, bias_s0 + 10 * 1024, b.acc_free, b.a_ready, b.a_ready + 16, lane);
       arrive_idle(b.acc_free + 8, b.a_ready + 8, lane);
       // ---- RGB (N = 16) -> raw ----
       wait_bar(b.acc_full, nfull[0]++ & 1, 350);
@@ -841,8 +863,9 @@ static inline int up(int v, int m) { return (v + m - 1) / m * m; }
 
 void tc_free(zest_net* net) {
   if (net->tc_blob) cudaFree(net->tc_blob);
+  if (net->tc_bias) cudaFree(net->tc_bias);
   if (net->tc_plan_host) delete (TcPlanHost*)net->tc_plan_host;
-  net->tc_blob = nullptr; net->tc_plan_host = nullptr;
+  net->tc_blob = nullptr; net->tc_bias = nullptr; net->tc_plan_host = nullptr;
 }
 
 static bool tc_supported(const zest_net* n) {
@@ -862,7 +885,7 @@ int tc_pack(zest_net* net, cudaStream_t st) {
   ph->gate_fp32 = (getenv("ZEST_TC_GATE_FP32") && atoi(getenv("ZEST_TC_GATE_FP32")) != 0) ? 1 : 0;
   const int Ppad = ph->Ppad, Fpad = ph->Fpad;
   // S = [PE | dirPE x 2 (4 + 4 chunks) | ones (2) | feats] + ring
-  ph->smem_bytes = (size_t)(Ppad / 8 + 10 + Fpad / 8) * kChunkBytes + (size_t)kStages * kStageBytes;
+  ph->smem_bytes = (size_t)(Ppad / 8 + 10 + Fpad / 8) * kChunkBytes + (kBiasInMma ? 0 : (size_t)kBiasOps * 1024) + (size_t)kStages * kStageBytes;
 
   std::vector<TcStage> stages;
   std::vector<PackDesc> packs;
@@ -876,24 +899,24 @@ int tc_pack(zest_net* net, cudaStream_t st) {
   };
   auto skip = [&]() { stages.push_back(TcStage{0u, 0u}); };
   // revolution 0: GATE part 0, 1 (feats) | L0 part 0, 1 (PE)
-  for (int part = 0; part < 2; ++part) stage(128, 128, net->w_gate, F, part * 128, 0, Fpad, F, net->b_gate);
-  for (int part = 0; part < 2; ++part) stage(128, 128, net->w_pts[0], P, part * 128, 0, Ppad, P, net->b_pts[0]);
+  for (int part = 0; part < 2; ++part) stage(128, 128, net->w_gate, F, part * 128, 0, Fpad, F, kBiasInMma ? net->b_gate : -1);
+  for (int part = 0; part < 2; ++part) stage(128, 128, net->w_pts[0], P, part * 128, 0, Ppad, P, kBiasInMma ? net->b_pts[0] : -1);
   // L1..L7: (p0, K lo) (p1, K lo) (p0, K hi + bias) (p1, K hi + bias); L5 = [pe | h4] starts with the PE blocks
   for (int l = 1; l < 8; ++l) {
     const int ld = (l == 5) ? P + W : W, c0 = (l == 5) ? P : 0;
     if (l == 5) for (int part = 0; part < 2; ++part) stage(128, 128, net->w_pts[l], ld, part * 128, 0, Ppad, P, -1);
     for (int part = 0; part < 2; ++part) stage(128, 128, net->w_pts[l], ld, part * 128, c0, 128, 128, -1);
-    for (int part = 0; part < 2; ++part) stage(128, 128, net->w_pts[l], ld, part * 128, c0 + 128, 128, 128, net->b_pts[l]);
+    for (int part = 0; part < 2; ++part) stage(128, 128, net->w_pts[l], ld, part * 128, c0 + 128, 128, 128, kBiasInMma ? net->b_pts[l] : -1);
     if (l == 5) { skip(); skip(); }
   }
   // FEAT, with the stacked small heads (N = 16) behind the low-K stages
   for (int part = 0; part < 2; ++part) stage(128, 128, net->w_feat, W, part * 128, 0, 128, 128, -1);
   stage(16, net->n_small, net->w_small, W, 0, 0, W, W, net->b_small);
-  for (int part = 0; part < 2; ++part) stage(128, 128, net->w_feat, W, part * 128, 128, 128, 128, net->b_feat);
+  for (int part = 0; part < 2; ++part) stage(128, 128, net->w_feat, W, part * 128, 128, 128, 128, kBiasInMma ? net->b_feat : -1);
   // VIEWS: [feature | dirPE] (N = 128); RGB (N = 16) from v
   stage(128, 128, net->w_views, W + Cv, 0, 0, 128, 128, -1);
   stage(128, 128, net->w_views, W + Cv, 0, 128, 128, 128, -1);
-  stage(128, 128, net->w_views, W + Cv, 0, W, 32, Cv, net->b_views);
+  stage(128, 128, net->w_views, W + Cv, 0, W, 32, Cv, kBiasInMma ? net->b_views : -1);
   stage(16, 3, net->w_rgb, W / 2, 0, 0, W / 2, W / 2, net->b_rgb);
   skip(); skip(); skip();
 
@@ -903,7 +926,18 @@ int tc_pack(zest_net* net, cudaStream_t st) {
 
   if (first) {
     ZEST_CUDA(cudaMalloc(&net->tc_blob, (size_t)blob_off));
+    ZEST_CUDA(cudaMalloc(&net->tc_bias, (size_t)kBiasOps * 256 * sizeof(float)));
     net->tc_bytes = blob_off;
+  }
+  {   // epilogue-side bias table: GATE, L0..L7, FEAT (256 each), VIEWS (128)
+    ZEST_CUDA(cudaMemsetAsync(net->tc_bias, 0, (size_t)kBiasOps * 256 * sizeof(float), st));
+    auto put = [&](int op, int64_t off, int n) {
+      return cudaMemcpyAsync(net->tc_bias + op * 256, net->f32 + off, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    };
+    ZEST_CUDA(put(0, net->b_gate, W));
+    for (int l = 0; l < 8; ++l) ZEST_CUDA(put(1 + l, net->b_pts[l], W));
+    ZEST_CUDA(put(9, net->b_feat, W));
+    ZEST_CUDA(put(10, net->b_views, W / 2));
   }
   // device-side scratch for the descriptors (freed after the pack kernel is enqueued + synced)
   PackDesc* d_packs = nullptr;
@@ -928,7 +962,7 @@ static int tc_launch(const zest_net* net, TcParams& p, cudaStream_t st) {
     return ZEST_E_ARG;
   }
   const TcPlanHost* ph = (const TcPlanHost*)net->tc_plan_host;
-  memcpy(p.plan, ph->stages.data(), ph->stages.size() * sizeof(TcStage)); p.n_stages = ph->n_stages; p.blob = (const uint8_t*)net->tc_blob;
+  memcpy(p.plan, ph->stages.data(), ph->stages.size() * sizeof(TcStage)); p.n_stages = ph->n_stages; p.blob = (const uint8_t*)net->tc_blob; p.bias = net->tc_bias;
   p.P = ph->P; p.Ppad = ph->Ppad; p.F = ph->F; p.Fpad = ph->Fpad;
   p.kind = net->kind; p.out_ch = net->out_ch; p.overlap = ph->overlap;
   p.n_tiles = (p.M + kTile - 1) / kTile;

@@ -27,6 +27,7 @@ struct zest_net {
   // ---- bf16 tensor-core image (built by mlp_tc.cu) ----
   void* tc_blob;       // device: weight stages in UMMA smem-image order
   int64_t tc_bytes;
+  float* tc_bias;      // device: [11][256] fp32 biases of the 256-wide ops, read by the tensor-core kernel's epilogue
   void* tc_plan_host;  // host: layer plan (opaque to everything but mlp_tc.cu)
 };
 

@@ -195,6 +195,16 @@ __device__ __forceinline__ void mul_f32x2(float& a0, float& a1, float b0, float 
       : "+f"(a0), "+f"(a1)
       : "f"(b0), "f"(b1));
 }
+// (a0, a1) += (b0, b1): one packed FADD2
+__device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb;\n\t"
+      "mov.b64 ra, {%0, %1};\n\t"
+      "mov.b64 rb, {%2, %3};\n\t"
+      "add.rn.f32x2 ra, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "f"(b0), "f"(b1));
+}
 // relu on a packed bf16 pair (HMNMX2.BF16)
 __device__ __forceinline__ uint32_t relu_bf16x2(uint32_t p) {
   uint32_t r;
@@ -213,6 +223,9 @@ __device__ __forceinline__ uint4 ld_smem_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
+}
+__device__ __forceinline__ void st_smem_u32(uint32_t addr, uint32_t a) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
 }
 __device__ __forceinline__ void st_smem_v2(uint32_t addr, uint32_t a, uint32_t b) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
