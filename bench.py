@@ -395,13 +395,21 @@ def main():
         host_out = {k: torch.empty((R, 3) if "rgb" in k else (R,), dtype=torch.float32).pin_memory() for k in keys}
         copy_stream = torch.cuda.Stream(device=dev)
 
+        def copy_slab(s):
+            a, b = s * per, min(R, (s + 1) * per)
+            with torch.cuda.stream(copy_stream):
+                slab = [h[:, a:b].to(dev, non_blocking=True) for h in host]
+                done = torch.cuda.Event(); done.record()
+            return slab, done
+
+        state = {"next": None}    # slab 0 of the next frame, copied while this frame's last slabs are still rendering
+
         def e2e_step():
-            pending = None
+            cur = state["next"] or copy_slab(0)
             for s in range(n_slabs):
                 a, b = s * per, min(R, (s + 1) * per)
-                with torch.cuda.stream(copy_stream):
-                    slab = [h[:, a:b].to(dev, non_blocking=True) for h in host]
-                    done = torch.cuda.Event(); done.record()
+                slab, done = cur
+                cur = copy_slab(s + 1) if s + 1 < n_slabs else None     # H2D of the next slab overlaps this slab's kernels
                 torch.cuda.current_stream().wait_event(done)
                 with torch.no_grad():
                     ret = rendering(sc.args, slab[0], slab[1], slab[2], slab[3], **kw)
@@ -409,10 +417,12 @@ def main():
                     host_out[k][a:b].copy_(ret[k][0], non_blocking=True)
                 for t_ in slab:
                     t_.record_stream(torch.cuda.current_stream())
+            state["next"] = copy_slab(0)          # the next frame's first slab rides under this frame's tail (inside the timed region)
             torch.cuda.current_stream().synchronize()
 
         for _ in range(2):
             e2e_step()
+        state["next"] = None      # every timed step's inputs are copied inside the timed region (the first step's slab 0 too)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n_e2e = max(2, args.steps // 2)
@@ -427,7 +437,7 @@ def main():
         h2d = sum(h.numel() * 4 for h in host)
         d2h = sum(v.numel() * 4 for v in host_out.values())
         e2e = {"value": world * R * n_e2e / (float(t_e2e) * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": n_e2e, "api": "zest_nerf_b200.renderer.rendering, 8 slabs/frame, pinned host rays"}
+               "d2h_bytes_per_step": d2h, "steps": n_e2e, "api": "zest_nerf_b200.renderer.rendering, 8 slabs/frame, pinned host rays, H2D of slab s+1 under the kernels of slab s"}
 
     # "next" row f1: the CUDA ray builder for one full frame (streaming writes: 28 B / sample + 12 B / ray), vs HBM peak
     f1 = None
