@@ -425,7 +425,7 @@ def main():
         state["next"] = None      # every timed step's inputs are copied inside the timed region (the first step's slab 0 too)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_e2e = max(2, args.steps // 2)
+        n_e2e = max(3, args.steps)
         e0.record()
         for _ in range(n_e2e):
             e2e_step()
