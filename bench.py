@@ -395,12 +395,22 @@ def main():
         host_out = {k: torch.empty((R, 3) if "rgb" in k else (R,), dtype=torch.float32).pin_memory() for k in keys}
         copy_stream = torch.cuda.Stream(device=dev)
 
+        # two persistent device staging sets (no allocation inside the timed loop: a cudaMalloc there synchronises the device)
+        stage_bufs = [[torch.empty((1, per) + tuple(h.shape[2:]), device=dev, dtype=torch.float32) for h in host] for _ in range(2)]
+        stage_free = [None, None]     # event: the kernels that last read this staging set have been enqueued and finished
+        flip = {"i": 0}
+
         def copy_slab(s):
             a, b = s * per, min(R, (s + 1) * per)
+            i = flip["i"]; flip["i"] ^= 1
             with torch.cuda.stream(copy_stream):
-                slab = [h[:, a:b].to(dev, non_blocking=True) for h in host]
+                if stage_free[i] is not None:
+                    copy_stream.wait_event(stage_free[i])
+                slab = [d[:, :b - a] for d in stage_bufs[i]]
+                for d, h in zip(slab, host):
+                    d.copy_(h[:, a:b], non_blocking=True)
                 done = torch.cuda.Event(); done.record()
-            return slab, done
+            return slab, done, i
 
         state = {"next": None}    # slab 0 of the next frame, copied while this frame's last slabs are still rendering
 
@@ -408,15 +418,14 @@ def main():
             cur = state["next"] or copy_slab(0)
             for s in range(n_slabs):
                 a, b = s * per, min(R, (s + 1) * per)
-                slab, done = cur
+                slab, done, i = cur
                 cur = copy_slab(s + 1) if s + 1 < n_slabs else None     # H2D of the next slab overlaps this slab's kernels
                 torch.cuda.current_stream().wait_event(done)
                 with torch.no_grad():
                     ret = rendering(sc.args, slab[0], slab[1], slab[2], slab[3], **kw)
                 for k in keys:
                     host_out[k][a:b].copy_(ret[k][0], non_blocking=True)
-                for t_ in slab:
-                    t_.record_stream(torch.cuda.current_stream())
+                stage_free[i] = torch.cuda.Event(); stage_free[i].record()
             state["next"] = copy_slab(0)          # the next frame's first slab rides under this frame's tail (inside the timed region)
             torch.cuda.current_stream().synchronize()
 
