@@ -17,6 +17,10 @@
  *   zest_mlp_fwd_tc                       same, bf16 tcgen05/TMEM tensor cores, PE fused in prologue
  *   zest_composite_static_fwd / _bwd      renderer.py:74-164 depth2dist + raw2alpha + raw2outputs
  *   zest_composite_blend_fwd / _bwd       renderer.py:166-219 raw2outputs_blending
+ *   zest_gather_mlp_fwd_tc                renderer.py:51-72 + 246-318 + 237-242 -> networks.py:150-221 in ONE
+ *                                         launch (gather + PE + tensor-core MLP): the inference hot path
+ *   zest_build_rays                       utils.py:133-230 get_rays_mvs + :290-394 build_rays_base +
+ *                                         :232-288 get_ndc_coordinate ("next" row f1)
  *
  * Conventions
  *   - Every pointer is a DEVICE pointer into memory owned by the caller (PyTorch); the library
