@@ -87,7 +87,7 @@ struct PackDesc {  // how to build one weight block image from the fp32 blob
 struct TcPlanHost {
   std::vector<TcStage> stages;
   int n_stages = 0;
-  int P, Ppad, F, Fpad, C, overlap, gate_fp32;
+  int P, Ppad, F, Fpad, C, overlap, gate_fp32, cluster2;
   size_t smem_bytes;
 };
 
@@ -257,7 +257,11 @@ struct MmaCtx {
   Bars b;
   uint32_t phase, par, n_issued;
   uint32_t ones_lo, ring_lo;
+  uint32_t pair;     // 1: this CTA shares its weight ring with the other CTA of a 2-CTA cluster (slot releases go to both)
   __device__ __forceinline__ void next_op() { par ^= 1u; }
+  __device__ __forceinline__ void release_slot(uint32_t bar) {   // elected lane: all MMAs reading the slot have been issued
+    if (pair) ptx::mma_commit_multicast(bar, (uint16_t)3); else ptx::mma_commit(bar);
+  }
   __device__ __forceinline__ void wait(uint32_t need) {
     if (need & 1u) wait_bar(b.a_ready, par, 200);
     if (need & 2u) wait_bar(b.a_ready + 8, par, 201);
@@ -304,7 +308,7 @@ __device__ __forceinline__ void mma_stage(MmaCtx& c, uint32_t a, int n_k16, uint
       b_lo += 2u * N;
     }
     if (bias) ptx::mma_bf16_ss(d_tmem, kHi | c.ones_lo, kHi | b_lo, kIdesc, 1u);
-    ptx::mma_commit(c.b.empty + 8 * SLOT);
+    c.release_slot(c.b.empty + 8 * SLOT);
     if (commit_part >= 0) ptx::mma_commit(c.b.acc_full + 8 * commit_part);
   }
   __syncwarp();
@@ -315,12 +319,16 @@ __device__ __forceinline__ void mma_stage(MmaCtx& c, uint32_t a, int n_k16, uint
 template <int SLOT>
 __device__ __forceinline__ void mma_skip(MmaCtx& c) {
   wait_bar(c.b.full + 8 * SLOT, c.phase, 230 + SLOT);
-  if (ptx::elect_one()) ptx::mbar_arrive(c.b.empty + 8 * SLOT);
+  if (ptx::elect_one()) {
+    ptx::mbar_arrive(c.b.empty + 8 * SLOT);
+    if (c.pair) ptx::mbar_arrive_remote(c.b.empty + 8 * SLOT, ptx::cluster_ctarank() ^ 1u);
+  }
   __syncwarp();
   ++c.n_issued;
 }
 
-template <int C, bool GATE32, int kLoadWarps>  // C = 3 (static: xyz) or 4 (dynamic: xyz + t); GATE32: fp32 gate multiply
+template <int C, bool GATE32, int kLoadWarps, int CL>  // C = 3 (static: xyz) or 4 (dynamic: xyz + t); GATE32: fp32 gate multiply;
+                                                       // CL = 2: CTA pairs (clusters) share every weight stage via TMA multicast
 __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_bars[2 * kStages + 10];
@@ -344,7 +352,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
   const uint32_t in_ready = b.a_ready + 24, feats_free = in_ready + 8, pe_free = in_ready + 16;
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(b.full + 8 * s, 1); ptx::mbar_init(b.empty + 8 * s, 1); }
+    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(b.full + 8 * s, 1); ptx::mbar_init(b.empty + 8 * s, CL); }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(b.acc_full + 8 * i, 1);
       ptx::mbar_init(b.acc_free + 8 * i, kEpiWarps);
@@ -370,7 +378,12 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = s_tmem;
-  const int64_t my_tiles = (p.n_tiles > blockIdx.x) ? (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // CL = 2: both CTAs of a pair walk the same number of tiles (the even CTA's count; a surplus tile has no valid row)
+  // because every weight stage is loaded half by each and multicast to both
+  const int64_t first_cta = (CL == 2) ? (blockIdx.x & ~1u) : blockIdx.x;
+  const int64_t my_tiles = (p.n_tiles > first_cta) ? (p.n_tiles - first_cta + gridDim.x - 1) / gridDim.x : 0;
+  const uint32_t cta_rank = (CL == 2) ? ptx::cluster_ctarank() : 0u;
+  if (CL == 2) ptx::cluster_sync();   // the peer's barriers are initialised before anything is multicast into this CTA
 
   if (warp == kEpiWarps) {
     // ===================== weight producer =====================
@@ -386,7 +399,11 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
           if (ptx::elect_one()) {
             if (bytes) {
               ptx::mbar_arrive_expect_tx(b.full + 8 * slot, bytes);
-              ptx::bulk_g2s(ring + slot * kStageBytes, p.blob + src_off, bytes, b.full + 8 * slot);
+              if (CL == 2)   // this CTA fetches its half of the stage and multicasts it into both rings
+                ptx::bulk_g2s_multicast(ring + slot * kStageBytes + cta_rank * (bytes / 2), p.blob + src_off + cta_rank * (bytes / 2), bytes / 2,
+                                        b.full + 8 * slot, (uint16_t)3);
+              else
+                ptx::bulk_g2s(ring + slot * kStageBytes, p.blob + src_off, bytes, b.full + 8 * slot);
             } else {
               ptx::mbar_arrive(b.full + 8 * slot);
             }
@@ -405,7 +422,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
     // at least once before its last commit.  The schedule is straight-line code that must walk the
     // ring stages in exactly the order tc_pack() laid them out (checked per tile against n_stages).
     int tl_n[2] = {0, 0}; (void)tl_n;
-    MmaCtx c{b, 0u, 1u, 0u, (((s_base + ones_chunk * kChunkBytes) >> 4) & 0x3FFF) | kALbo, (ring >> 4) & 0x3FFF};
+    MmaCtx c{b, 0u, 1u, 0u, (((s_base + ones_chunk * kChunkBytes) >> 4) & 0x3FFF) | kALbo, (ring >> 4) & 0x3FFF, (uint32_t)(CL == 2)};
     const uint32_t pe_lo = ((s_base >> 4) & 0x3FFF) | kALbo;
     const uint32_t dir_lo[2] = {pe_lo + dir_chunk * (kChunkBytes >> 4), pe_lo + (dir_chunk + 4) * (kChunkBytes >> 4)};
     const uint32_t feat_lo = pe_lo + feat_chunk * (kChunkBytes >> 4);
@@ -718,6 +735,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL == 2) ptx::cluster_sync();   // no CTA leaves while its peer may still multicast into it / arrive on its barriers
   if (warp == kEpiWarps + 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 512); }
 }
 
@@ -882,6 +900,7 @@ int tc_pack(zest_net* net, cudaStream_t st) {
   const int W = 256, P = net->in_pts, F = net->in_feat, Cv = net->in_views;
   ph->P = P; ph->Ppad = up(P, 32); ph->F = F; ph->Fpad = up(F, 16); ph->C = (P == 84) ? 4 : 3;
   ph->overlap = overlap ? 1 : 0;
+  ph->cluster2 = (getenv("ZEST_TC_CLUSTER") && atoi(getenv("ZEST_TC_CLUSTER")) == 2) ? 1 : 0;
   ph->gate_fp32 = (getenv("ZEST_TC_GATE_FP32") && atoi(getenv("ZEST_TC_GATE_FP32")) != 0) ? 1 : 0;
   const int Ppad = ph->Ppad, Fpad = ph->Fpad;
   // S = [PE | dirPE x 2 (4 + 4 chunks) | ones (2) | feats] + ring
@@ -967,14 +986,31 @@ static int tc_launch(const zest_net* net, TcParams& p, cudaStream_t st) {
   p.kind = net->kind; p.out_ch = net->out_ch; p.overlap = ph->overlap;
   p.n_tiles = (p.M + kTile - 1) / kTile;
   if (p.M == 0) return ZEST_OK;
-  const int grid = (int)(p.n_tiles < num_sms() ? p.n_tiles : num_sms());
+  int grid = (int)(p.n_tiles < num_sms() ? p.n_tiles : num_sms());
+  const bool wide = p.vol && p.V > 6;   // many source views: the in-kernel gather needs four loader warps
+  // ZEST_TC_CLUSTER=2 (experiment, default off): CTA pairs share every weight stage through TMA multicast, halving the
+  // L2 -> SM weight traffic.  Measured 7 % SLOWER on cfg2 (same-box A/B): the pair runs in lock step on a ring that is
+  // one layer deep, so any skew between the two CTAs stalls both; kept for the common variant only.
+  const bool pair = ph->cluster2 && p.n_tiles >= 2 && !wide && !ph->gate_fp32;
+  if (pair) grid = (grid + 1) & ~1;   // whole clusters; a CTA without tiles of its own still mirrors its peer's stage walk
 #define ZEST_TC_GO(CC, G32, LW)                                                                                              \
   do {                                                                                                                       \
-    ZEST_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<CC, G32, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ph->smem_bytes)); \
-    mlp_tc_kernel<CC, G32, LW><<<grid, 32 * (kEpiWarps + 2 + LW), ph->smem_bytes, st>>>(p);                                  \
+    ZEST_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<CC, G32, LW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ph->smem_bytes)); \
+    mlp_tc_kernel<CC, G32, LW, 1><<<grid, 32 * (kEpiWarps + 2 + LW), ph->smem_bytes, st>>>(p);                               \
   } while (0)
-  const bool wide = p.vol && p.V > 6;   // many source views: the in-kernel gather needs four loader warps
-  if (ph->C == 3) {
+#define ZEST_TC_GO_PAIR(CC)                                                                                                  \
+  do {                                                                                                                       \
+    ZEST_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<CC, false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ph->smem_bytes)); \
+    cudaLaunchConfig_t cfg = {};                                                                                             \
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(32 * (kEpiWarps + 2 + 2)); cfg.dynamicSmemBytes = ph->smem_bytes; cfg.stream = st; \
+    cudaLaunchAttribute at[1];                                                                                               \
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1; \
+    cfg.attrs = at; cfg.numAttrs = 1;                                                                                        \
+    ZEST_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<CC, false, 2, 2>, p));                                                  \
+  } while (0)
+  if (pair) {
+    if (ph->C == 3) ZEST_TC_GO_PAIR(3); else ZEST_TC_GO_PAIR(4);
+  } else if (ph->C == 3) {
     if (ph->gate_fp32) { if (wide) ZEST_TC_GO(3, true, 4); else ZEST_TC_GO(3, true, 2); }
     else { if (wide) ZEST_TC_GO(3, false, 4); else ZEST_TC_GO(3, false, 2); }
   } else {
@@ -982,6 +1018,7 @@ static int tc_launch(const zest_net* net, TcParams& p, cudaStream_t st) {
     else { if (wide) ZEST_TC_GO(4, false, 4); else ZEST_TC_GO(4, false, 2); }
   }
 #undef ZEST_TC_GO
+#undef ZEST_TC_GO_PAIR
   ZEST_LAUNCH_CHECK();
   return ZEST_OK;
 }

@@ -74,6 +74,32 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
       : "memory");
 }
 
+// ---------------------------------------------------------------- thread-block clusters
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of this cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta)
+      : "memory");
+}
+// 1-D bulk copy global -> the same shared-memory offset of every CTA in cta_mask; each destination CTA's mbarrier
+// (same offset) receives the complete_tx for the bytes written into it
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
@@ -117,6 +143,13 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// the same arrival, delivered to the mbarrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void mma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
 }
 
 // K-major, no-swizzle ("interleaved") shared-memory matrix descriptor.
