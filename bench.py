@@ -463,7 +463,8 @@ def main():
         f1_ms = e0.elapsed_time(e1) / 5
         byts = R * S * 28 + R * 12
         f1 = {"kernel": "build_rays_kernel (zest_build_rays)", "ms_per_frame": f1_ms, "achieved_gbs": byts / f1_ms / 1e6,
-              "peak_gbs": pk["hbm_gbs"], "frac": byts / f1_ms / 1e6 / pk["hbm_gbs"], "bytes_per_frame": byts}
+              "peak_gbs": pk["hbm_gbs"], "frac": byts / f1_ms / 1e6 / pk["hbm_gbs"], "bytes_per_frame": byts,
+              "note": "write-only stream (28 B/sample); the peak is the measured read+write copy bandwidth"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -82,10 +82,12 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
     }
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM + 4]);
-      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * TN]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * TN + 4]);
+      // micro-tile = rows {4 ty .. +3, 64 + 4 ty .. +3} x columns {4 tx .. +3, 64 + 4 tx .. +3}: the 16 lanes that differ in tx
+      // read 16 consecutive float4 (conflict-free); an 8-wide contiguous column run per lane is a 2-way bank conflict
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
       const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
@@ -104,11 +106,11 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
   const bool atomic = g.splits > 1;
 #pragma unroll
   for (int p = 0; p < TM; ++p) {
-    const int64_t i = i0 + ty * TM + p;
+    const int64_t i = i0 + (p < 4 ? ty * 4 + p : 64 + ty * 4 + (p - 4));
     if (i >= g.I) continue;
 #pragma unroll
     for (int q = 0; q < TN; ++q) {
-      const int64_t j = j0 + tx * TN + q;
+      const int64_t j = j0 + (q < 4 ? tx * 4 + q : 64 + tx * 4 + (q - 4));
       if (j >= g.J) continue;
       float v = acc[p][q];
       if (g.bias && blockIdx.z == 0) v += __ldg(g.bias + j);
