@@ -397,6 +397,41 @@ def test_ray_sharding_is_bit_identical(zops):
         assert torch.equal(full[k], torch.cat([p[k] for p in parts], 1)), k
 
 
+def test_full_size_frame_properties(zops):
+    """BASELINE cfg2 at full size (288 x 512 x 128 samples, static + dynamic): the oracle cannot finish this in seconds,
+    so the bar is size-independent properties - ray sharding (rendering the frame in 3 uneven slabs == one launch, bit for
+    bit), compositing invariants (weights in [0,1], rgb a convex combination of sigmoids, depth within [near, far]), and
+    the bf16 render against the fp32 render of the same kernels family (PSNR)."""
+    from zest_nerf_b200 import rays as zrays
+    from zest_nerf_b200.driver import FrameRenderer
+    from zest_nerf_b200.synthetic import make_scene
+    sc = make_scene(H=288, W=512, V=3, pad=24, D=128, dynamic=True, seed=0)
+    sc.to(DEV)
+    pts, rdir, ndc, z = zops.build_rays(sc.H, sc.W, sc.w2cs, sc.c2ws, sc.intrinsics, sc.near_fars, 128, pad=24, device=DEV)
+    fr = FrameRenderer(sc.net_static, sc.net_dynamic, device=DEV)
+    fr.set_frame(sc.vol_static, sc.imgs[:, :-1].contiguous(), sc.im_cam_mat, sc.vol_dynamic, sc.nb_imgs, sc.nb_cam_mat)
+    R = sc.H * sc.W
+    full = fr.render_rays(pts, ndc, z, rdir, sc.ref_frame_idx)
+    cuts = (0, 50001, 99872, R)
+    parts = [fr.render_rays(pts[:, a:b], ndc[:, a:b], z[:, a:b], rdir[:, a:b], sc.ref_frame_idx) for a, b in zip(cuts[:-1], cuts[1:])]
+    torch.cuda.synchronize()
+    for k, v in full.items():
+        assert torch.equal(v, torch.cat([p_[k] for p_ in parts], 1)), k
+        assert torch.isfinite(v).all(), k
+    for k in ("rgb_map", "rgb_map_ref", "rgb_map_ref_dy"):
+        assert float(full[k].min()) >= 0.0 and float(full[k].max()) <= 1.0 + 1e-5, k
+    assert float(full["weights_map_dd"].min()) >= 0.0 and float(full["weights_map_dd"].max()) <= 1.0 + 1e-5
+    cos = rdir.norm(dim=-1)
+    for k in ("depth_map", "depth_map_ref"):      # sum_i w_i z_i with sum w <= 1 and z in [near, far]
+        assert float((full[k] - 6.0 * 1.0001).max()) <= 0.0 and float(full[k].min()) >= 0.0, k
+    with zops.mlp_mode("fp32"):
+        ref32 = fr.render_rays(pts, ndc, z, rdir, sc.ref_frame_idx)
+    torch.cuda.synchronize()
+    for k in ("rgb_map", "rgb_map_ref"):
+        assert psnr(full[k][0].cpu(), ref32[k][0].cpu()) >= 40.0, k
+        assert float((full[k] - ref32[k]).abs().max()) <= 3e-2, k
+
+
 def test_unsupported_modes_raise(zops):
     from zest_nerf_b200.renderer import rendering
     sc, rays, mode, _ = build_case("static_val")
