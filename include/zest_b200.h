@@ -200,6 +200,22 @@ int zest_tc_set_timeline(unsigned long long* buf);
 /* Characterisation probe: one CTA issues reps x 16 back-to-back UMMAs (M = 128, N, K = 16; ts = A from
  * TMEM), optionally under TMEM-load traffic from its other warps.  out[0] = cycles to completion. */
 int zest_tc_rate_probe(int N, int reps, int ts, int ld_traffic, long long* out, void* stream);
+/* GEMM engine of the fp32 MLP path (zest_mlp_fwd_f32 / _bwd_f32).  The tensor-core engines split every fp32 operand
+ * into head + residual on the fly and issue three UMMAs per product (fp32 accumulate in TMEM):
+ *   2 (default) = tcgen05 3 x tf32 (22 operand bits) with the head product and the cross products in separate TMEM
+ *       accumulators (the tensor core's fp32 accumulate truncates; this keeps the bias at the fp32 level): gradients of
+ *       the 4096-ray fine-tune batch agree with reference autograd to 8e-4 rel L2, like the CUDA-core engine (8e-4);
+ *   1 = tcgen05 3 x bf16 (16 operand bits, one accumulator): 1.4x faster, 3.6e-3 on the same gradients;
+ *   0 = exact-fp32 CUDA-core kernel (3.8x slower than 1).
+ * Returns the previous engine.  Env ZEST_GEMM=simt|bf16x3 selects 0|1 at load. */
+int zest_set_gemm_engine(int engine);
+/* Unit-test hook for all engines: C[I,J] (+)= sum_k A[i*sa_i + k*sa_k] * B[j*sb_j + k*sb_k] (+ bias[j]); splits > 1
+ * splits the K range over CTAs (atomic accumulation into C, which the caller zeroes or pre-fills).  b_scratch
+ * (optional, device, b_scratch_bytes >= ceil(J/256) * ceil(K/16) * 32 KiB) lets the tensor-core engines pack B into
+ * UMMA stage images once and stream it by TMA (the MLP path does this for its weight operands). */
+int zest_gemm_f32(const float* A, int64_t sa_i, int64_t sa_k, const float* B, int64_t sb_j, int64_t sb_k,
+                  float* C, int64_t ldc, int64_t I, int J, int64_t K, const float* bias, int accumulate,
+                  int splits, int engine, void* b_scratch, int64_t b_scratch_bytes, void* stream);
 /* How many kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t zest_launch_count(void);
 

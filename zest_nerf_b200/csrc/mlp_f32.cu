@@ -30,6 +30,8 @@ struct F32Plan {
   int ldX5, ldVX;
   int64_t G, X5, H[16], Z[16], VX, V128, SH, RGB;           // forward
   int64_t gHa, gHb, dZ, gG, gX5, gVX, gV128, gSH, gRGB;      // backward scratch (train only)
+  int64_t PACK;                                               // weight-operand stage images of the tensor-core GEMM
+  static constexpr int64_t kPackFloats = 512 * 1024;          // 2 MiB >= 2 column tiles x 22 K stages x 32 KiB
   int64_t total;
   F32Plan(const zest_net* n, int64_t M, bool train) {
     W = n->width; P = n->in_pts; F = n->in_feat; Cv = n->in_views; D = n->depth; skip = n->skip; ns = n->n_small;
@@ -48,8 +50,16 @@ struct F32Plan {
       gHa = take(W); gHb = take(W); dZ = take(W); gG = take(W); gX5 = take(ldX5); gVX = take(ldVX);
       gV128 = take(W / 2); gSH = take(16); gRGB = take(4);
     }
+    PACK = o; o += kPackFloats;
     total = o;
   }
+};
+
+// scratch of the GEMM in flight (stream-ordered reuse: one pack kernel + one GEMM at a time per stream)
+static thread_local void* t_pack = nullptr;
+struct PackScope {
+  PackScope(float* ws, const F32Plan& p) { t_pack = ws + p.PACK; }
+  ~PackScope() { t_pack = nullptr; }
 };
 
 __global__ void finalize_fwd_kernel(const float* __restrict__ rgb, const float* __restrict__ sh, int kind,
@@ -92,41 +102,9 @@ __global__ void finalize_bwd_kernel(const float* __restrict__ graw, const float*
   }
 }
 
-// dZ = gH * 1[H>0] * G ;  gG += gH * 1[H>0] * Z
-__global__ void gate_bwd_kernel(const float* __restrict__ gH, int64_t ldgh, const float* __restrict__ H, int64_t ldh,
-                                const float* __restrict__ Z, const float* __restrict__ G, int64_t M, int W,
-                                float* __restrict__ dZ, float* __restrict__ gG) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M * W) return;
-  const int64_t m = i / W;
-  const int j = (int)(i - m * W);
-  const float g = (H[m * ldh + j] > 0.f) ? gH[m * ldgh + j] : 0.f;
-  dZ[i] = g * G[i];
-  gG[i] += g * Z[i];
-}
-
 __global__ void relu_mask_kernel(float* __restrict__ g, const float* __restrict__ y, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && !(y[i] > 0.f)) g[i] = 0.f;
-}
-
-// out[j] += sum_m X[m*ld + j], j < J (J <= 1024).  Each block reduces a slab of rows.
-__global__ void colsum_kernel(const float* __restrict__ X, int64_t ld, int64_t M, int J, float* out) {
-  const int64_t rows_per = (M + gridDim.x - 1) / gridDim.x;
-  const int64_t m0 = blockIdx.x * rows_per, m1 = (m0 + rows_per < M) ? m0 + rows_per : M;
-  for (int j = threadIdx.x; j < J; j += blockDim.x) {
-    float s = 0.f;
-    for (int64_t m = m0; m < m1; ++m) s += X[m * ld + j];
-    atomicAdd(out + j, s);
-  }
-}
-
-static int colsum(const float* X, int64_t ld, int64_t M, int J, float* out, cudaStream_t st) {
-  if (!out) return ZEST_OK;
-  const unsigned grid = (unsigned)((M + 511) / 512 < 1024 ? (M + 511) / 512 : 1024);
-  colsum_kernel<<<grid, 256, 0, st>>>(X, ld, M, J, out);
-  ZEST_LAUNCH_CHECK();
-  return ZEST_OK;
 }
 
 static int copy2d(float* dst, int64_t ldd, const float* src, int64_t lds, int cols, int64_t M, cudaStream_t st) {
@@ -145,6 +123,7 @@ static GemmArgs linear(const float* x, int64_t ldx, const float* W, int J, int64
   a.A = x; a.sa_i = ldx; a.sa_k = 1;
   a.B = W; a.sb_j = K; a.sb_k = 1;
   a.C = y; a.ldc = ldy; a.I = M; a.J = J; a.K = K; a.bias = b;
+  a.b_scratch = t_pack; a.b_scratch_bytes = t_pack ? F32Plan::kPackFloats * (int64_t)sizeof(float) : 0;
   return a;
 }
 // gx = gy @ W  with W [N, J] row-major: reduce over N
@@ -154,15 +133,16 @@ static GemmArgs linear_bwd_x(const float* gy, int64_t ldgy, const float* W, int 
   a.A = gy; a.sa_i = ldgy; a.sa_k = 1;
   a.B = W; a.sb_j = 1; a.sb_k = J;
   a.C = gx; a.ldc = ldgx; a.I = M; a.J = J; a.K = N; a.accumulate = accumulate;
+  a.b_scratch = t_pack; a.b_scratch_bytes = t_pack ? F32Plan::kPackFloats * (int64_t)sizeof(float) : 0;
   return a;
 }
-// gW [N, J] += gy^T @ x : reduce over the M rows, split across grid.z
+// gW [N, J] += gy^T @ x : reduce over the M rows, split across grid.z;  gb [N] += column sums of gy (bias gradient)
 static GemmArgs linear_bwd_w(const float* gy, int64_t ldgy, int N, const float* x, int64_t ldx, int J, float* gW,
-                             int64_t M) {
+                             int64_t M, float* gb) {
   GemmArgs a{};
   a.A = gy; a.sa_i = 1; a.sa_k = ldgy;
   a.B = x; a.sb_j = 1; a.sb_k = ldx;
-  a.C = gW; a.ldc = J; a.I = N; a.J = J; a.K = M; a.accumulate = 1;
+  a.C = gW; a.ldc = J; a.I = N; a.J = J; a.K = M; a.accumulate = 1; a.rowsum = gb;
   int64_t s = M / 2048;
   a.splits = (int)(s < 2 ? 2 : (s > 256 ? 256 : s));
   return a;
@@ -259,6 +239,7 @@ extern "C" int zest_mlp_fwd_f32(const zest_net* net, const float* x, int ldx, in
   cudaStream_t st = (cudaStream_t)stream;
   const F32Plan p(net, M, train != 0);
   float* ws = (float*)workspace;
+  const PackScope pack_scope(ws, p);
   const float* w = net->f32;
   const int W = p.W, P = p.P;
   float* G = ws + p.G;
@@ -295,6 +276,7 @@ extern "C" int zest_mlp_bwd_f32(const zest_net* net, const float* x, int ldx, in
   cudaStream_t st = (cudaStream_t)stream;
   const F32Plan p(net, M, true);
   float* ws = (float*)workspace;
+  const PackScope pack_scope(ws, p);
   const float* w = net->f32;
   const int W = p.W, P = p.P, D = p.D;
   auto gp = [&](int idx) -> float* { return gparams ? gparams[idx] : nullptr; };
@@ -307,58 +289,66 @@ extern "C" int zest_mlp_bwd_f32(const zest_net* net, const float* x, int ldx, in
   finalize_bwd_kernel<<<gm, 256, 0, st>>>(graw, SH, net->kind, M, net->out_ch, gRGB, gSH);
   ZEST_LAUNCH_CHECK();
   // rgb_linear
-  if (gp(I_RGB)) { ZEST_TRY(launch_gemm(linear_bwd_w(gRGB, 4, 3, V128, W / 2, W / 2, gp(I_RGB), M), st)); ZEST_TRY(colsum(gRGB, 4, M, 3, gp(I_RGB + 1), st)); }
+  if (gp(I_RGB)) ZEST_TRY(launch_gemm(linear_bwd_w(gRGB, 4, 3, V128, W / 2, W / 2, gp(I_RGB), M, gp(I_RGB + 1)), st));
   ZEST_TRY(launch_gemm(linear_bwd_x(gRGB, 4, w + net->w_rgb, 3, W / 2, gV128, W / 2, M, 0), st));
   relu_mask_kernel<<<(unsigned)((M * (W / 2) + 255) / 256), 256, 0, st>>>(gV128, V128, M * (W / 2));
   ZEST_LAUNCH_CHECK();
   // views_linears[0]
-  if (gp(I_VIEWS)) { ZEST_TRY(launch_gemm(linear_bwd_w(gV128, W / 2, W / 2, VX, p.ldVX, W + p.Cv, gp(I_VIEWS), M), st)); ZEST_TRY(colsum(gV128, W / 2, M, W / 2, gp(I_VIEWS + 1), st)); }
+  if (gp(I_VIEWS)) ZEST_TRY(launch_gemm(linear_bwd_w(gV128, W / 2, W / 2, VX, p.ldVX, W + p.Cv, gp(I_VIEWS), M, gp(I_VIEWS + 1)), st));
   ZEST_TRY(launch_gemm(linear_bwd_x(gV128, W / 2, w + net->w_views, W / 2, W + p.Cv, gVX, p.ldVX, M, 0), st));
   // last hidden activation
   const int last = D - 1;
-  const float* Hl = (last == p.skip) ? X5 + P : ws + p.H[last];
-  const int64_t ldHl = (last == p.skip) ? p.ldX5 : W;
+  const float* Hl = ws + p.H[last];   // zest_net_create guarantees skip < depth - 1
+  const int64_t ldHl = W;
   // feature_linear and the stacked small heads feed gH of the last layer
-  if (gp(I_FEAT)) { ZEST_TRY(launch_gemm(linear_bwd_w(gVX, p.ldVX, W, Hl, ldHl, W, gp(I_FEAT), M), st)); ZEST_TRY(colsum(gVX, p.ldVX, M, W, gp(I_FEAT + 1), st)); }
+  if (gp(I_FEAT)) ZEST_TRY(launch_gemm(linear_bwd_w(gVX, p.ldVX, W, Hl, ldHl, W, gp(I_FEAT), M, gp(I_FEAT + 1)), st));
   ZEST_TRY(launch_gemm(linear_bwd_x(gVX, p.ldVX, w + net->w_feat, W, W, gHa, W, M, 0), st));
-  if (gp(I_ALPHA)) { ZEST_TRY(launch_gemm(linear_bwd_w(gSH, 16, 1, Hl, ldHl, W, gp(I_ALPHA), M), st)); ZEST_TRY(colsum(gSH, 16, M, 1, gp(I_ALPHA + 1), st)); }
+  if (gp(I_ALPHA)) ZEST_TRY(launch_gemm(linear_bwd_w(gSH, 16, 1, Hl, ldHl, W, gp(I_ALPHA), M, gp(I_ALPHA + 1)), st));
   if (net->kind == 1 && gp(I_EXTRA)) {
-    ZEST_TRY(launch_gemm(linear_bwd_w(gSH + 1, 16, 1, Hl, ldHl, W, gp(I_EXTRA), M), st)); ZEST_TRY(colsum(gSH + 1, 16, M, 1, gp(I_EXTRA + 1), st));
+    ZEST_TRY(launch_gemm(linear_bwd_w(gSH + 1, 16, 1, Hl, ldHl, W, gp(I_EXTRA), M, gp(I_EXTRA + 1)), st));
   } else if (net->kind == 2 && gp(I_EXTRA)) {
-    ZEST_TRY(launch_gemm(linear_bwd_w(gSH + 1, 16, 6, Hl, ldHl, W, gp(I_EXTRA), M), st)); ZEST_TRY(colsum(gSH + 1, 16, M, 6, gp(I_EXTRA + 1), st));
-    ZEST_TRY(launch_gemm(linear_bwd_w(gSH + 7, 16, 2, Hl, ldHl, W, gp(I_EXTRA + 2), M), st)); ZEST_TRY(colsum(gSH + 7, 16, M, 2, gp(I_EXTRA + 3), st));
+    ZEST_TRY(launch_gemm(linear_bwd_w(gSH + 1, 16, 6, Hl, ldHl, W, gp(I_EXTRA), M, gp(I_EXTRA + 1)), st));
+    ZEST_TRY(launch_gemm(linear_bwd_w(gSH + 7, 16, 2, Hl, ldHl, W, gp(I_EXTRA + 2), M, gp(I_EXTRA + 3)), st));
   }
-  ZEST_TRY(launch_gemm(linear_bwd_x(gSH, 16, w + net->w_small, p.ns, W, gHa, W, M, 1), st));
-
+  // Every GEMM that produces the gradient wrt a hidden activation h_i = relu(z_i * g) applies that layer's gate backward in
+  // its epilogue (GemmArgs::gb_*): it writes dZ_i = gH_i 1[z_i g > 0] g and accumulates gG += gH_i 1[..] z_i; gH_i itself
+  // never reaches memory.  dZ ping-pongs between two buffers (a GEMM cannot overwrite its own A operand).
   ZEST_CUDA(cudaMemsetAsync(gG, 0, (size_t)M * W * sizeof(float), st));
-  float* gH = gHa; int64_t ldgH = W;
-  float* other = gHb;
-  bool gx_pe_written = false;
+  float* dZ_cur = dZ;
+  float* dZ_next = gHb;
+  auto fuse_gate = [&](GemmArgs& a, int layer, int col0, float* out) {
+    a.gb_Z = ws + p.Z[layer]; a.gb_G = G; a.gb_gG = gG; a.gb_dZ = out; a.gb_ld = W; a.gb_col0 = col0;
+  };
+  {
+    GemmArgs a = linear_bwd_x(gSH, 16, w + net->w_small, p.ns, W, gHa, W, M, 1);   // + feature_linear's part already in gHa
+    fuse_gate(a, last, 0, dZ_cur);
+    ZEST_TRY(launch_gemm(a, st));
+  }
   for (int i = D - 1; i >= 0; --i) {
-    const float* Hi = (i == p.skip) ? X5 + P : ws + p.H[i];
-    const int64_t ldHi = (i == p.skip) ? p.ldX5 : W;
-    gate_bwd_kernel<<<(unsigned)((M * W + 255) / 256), 256, 0, st>>>(gH, ldgH, Hi, ldHi, ws + p.Z[i], G, M, W, dZ, gG);
-    ZEST_LAUNCH_CHECK();
     // layer input
     const float* in; int64_t ld_in; const int K = in_layer(net, i);
     if (i == 0) { in = x; ld_in = ldx; }
     else if (i == p.skip + 1) { in = X5; ld_in = p.ldX5; }
     else { in = (i - 1 == p.skip) ? X5 + P : ws + p.H[i - 1]; ld_in = (i - 1 == p.skip) ? p.ldX5 : W; }
-    if (gp(2 * i)) { ZEST_TRY(launch_gemm(linear_bwd_w(dZ, W, W, in, ld_in, K, gp(2 * i), M), st)); ZEST_TRY(colsum(dZ, W, M, W, gp(2 * i + 1), st)); }
+    if (gp(2 * i)) ZEST_TRY(launch_gemm(linear_bwd_w(dZ_cur, W, W, in, ld_in, K, gp(2 * i), M, gp(2 * i + 1)), st));
     if (i == 0) {
-      if (gx) ZEST_TRY(launch_gemm(linear_bwd_x(dZ, W, w + net->w_pts[0], W, P, gx, ldx, M, gx_pe_written ? 1 : 0), st));
+      if (gx) ZEST_TRY(launch_gemm(linear_bwd_x(dZ_cur, W, w + net->w_pts[0], W, P, gx, ldx, M, 1), st));   // + the skip's part
     } else if (i == p.skip + 1) {
-      ZEST_TRY(launch_gemm(linear_bwd_x(dZ, W, w + net->w_pts[i], W, K, gX5, p.ldX5, M, 0), st));
-      if (gx) { ZEST_TRY(copy2d(gx, ldx, gX5, p.ldX5, P, M, st)); gx_pe_written = true; }
-      gH = gX5 + P; ldgH = p.ldX5;
+      // input = [pe | h_skip]: columns < P are d/d pe (kept in gX5, added to gx below), the rest is gH of layer `skip`
+      GemmArgs a = linear_bwd_x(dZ_cur, W, w + net->w_pts[i], W, K, gX5, p.ldX5, M, 0);
+      fuse_gate(a, i - 1, P, dZ_next);
+      ZEST_TRY(launch_gemm(a, st));
+      if (gx) ZEST_TRY(copy2d(gx, ldx, gX5, p.ldX5, P, M, st));
+      float* t = dZ_cur; dZ_cur = dZ_next; dZ_next = t;
     } else {
-      ZEST_TRY(launch_gemm(linear_bwd_x(dZ, W, w + net->w_pts[i], W, K, other, W, M, 0), st));
-      float* prev = (gH == gHa || gH == gHb) ? gH : ((other == gHa) ? gHb : gHa);
-      gH = other; ldgH = W; other = prev;
+      GemmArgs a = linear_bwd_x(dZ_cur, W, w + net->w_pts[i], W, K, gHa, W, M, 0);   // C unused: every column is fused
+      fuse_gate(a, i - 1, 0, dZ_next);
+      ZEST_TRY(launch_gemm(a, st));
+      float* t = dZ_cur; dZ_cur = dZ_next; dZ_next = t;
     }
   }
   // gate (pts_bias)
-  if (gp(I_GATE)) { ZEST_TRY(launch_gemm(linear_bwd_w(gG, W, W, x + P, ldx, p.F, gp(I_GATE), M), st)); ZEST_TRY(colsum(gG, W, M, W, gp(I_GATE + 1), st)); }
+  if (gp(I_GATE)) ZEST_TRY(launch_gemm(linear_bwd_w(gG, W, W, x + P, ldx, p.F, gp(I_GATE), M, gp(I_GATE + 1)), st));
   if (gx) {
     ZEST_TRY(launch_gemm(linear_bwd_x(gG, W, w + net->w_gate, W, p.F, gx + P, ldx, M, 0), st));
     ZEST_TRY(copy2d(gx + P + p.F, ldx, gVX + W, p.ldVX, p.Cv, M, st));

@@ -118,6 +118,15 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
       if (g.gate) v *= __ldg(g.gate + i * g.ldg + j);
       if (g.relu) v = fmaxf(v, 0.f);
       float* c = g.C + i * g.ldc + j;
+      if (g.gb_dZ && j >= g.gb_col0) {
+        if (g.accumulate) v += *c;
+        const int64_t o = i * g.gb_ld + (j - g.gb_col0);
+        const float zz = __ldg(g.gb_Z + o), gg = __ldg(g.gb_G + o);
+        const float m = (zz * gg > 0.f) ? v : 0.f;
+        g.gb_dZ[o] = m * gg;
+        g.gb_gG[o] += m * zz;
+        continue;
+      }
       if (atomic) atomicAdd(c, v);
       else if (g.accumulate) *c += v;
       else *c = v;
@@ -125,15 +134,38 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
   }
 }
 
-int launch_gemm(const GemmArgs& a, cudaStream_t st) {
+// rowsum[i] += sum_k A[i + k * ld], i < I (I <= 1024): each block reduces a slab of k
+__global__ void rowsum_kernel(const float* __restrict__ A, int64_t ld, int64_t K, int I, float* out) {
+  const int64_t per = (K + gridDim.x - 1) / gridDim.x;
+  const int64_t k0 = blockIdx.x * per, k1 = (k0 + per < K) ? k0 + per : K;
+  for (int i = threadIdx.x; i < I; i += blockDim.x) {
+    float s = 0.f;
+    for (int64_t k = k0; k < k1; ++k) s += A[k * ld + i];
+    atomicAdd(out + i, s);
+  }
+}
+
+int launch_gemm_simt(const GemmArgs& a, cudaStream_t st) {
   ZEST_CHECK_ARG(a.A && a.B && a.C && a.I >= 0 && a.J > 0 && a.K >= 0 && a.splits >= 1, "gemm: bad arguments");
-  ZEST_CHECK_ARG(a.splits == 1 || (!a.Z && !a.gate && !a.relu), "gemm: split-K cannot fuse a non-linear epilogue");
+  ZEST_CHECK_ARG(a.splits == 1 || (!a.Z && !a.gate && !a.relu && !a.gb_dZ), "gemm: split-K cannot fuse a non-linear epilogue");
+  ZEST_CHECK_ARG(!a.rowsum || a.sa_i == 1, "gemm: rowsum needs A with unit stride along its rows");
   if (a.I == 0) return ZEST_OK;
+  if (a.rowsum && a.K > 0) {
+    const unsigned rg = (unsigned)((a.K + 511) / 512 < 1024 ? (a.K + 511) / 512 : 1024);
+    rowsum_kernel<<<rg, 256, 0, st>>>(a.A, a.sa_k, a.K, (int)a.I, a.rowsum);
+    ZEST_LAUNCH_CHECK();
+  }
   dim3 grid((unsigned)((a.I + BM - 1) / BM), (unsigned)((a.J + BN - 1) / BN), (unsigned)a.splits);
   ZEST_CHECK_ARG(grid.y < 65536 && (a.I + BM - 1) / BM < (1ll << 31), "gemm: shape too large for one launch");
   sgemm_kernel<<<grid, 256, 0, st>>>(a);
   ZEST_LAUNCH_CHECK();
   return ZEST_OK;
+}
+
+int launch_gemm(const GemmArgs& a, cudaStream_t st) {
+  const int e = gemm_engine();
+  if (e >= 1 && gemm_tc_supported(a)) return launch_gemm_tc(a, e, st);
+  return launch_gemm_simt(a, st);
 }
 
 }  // namespace zest

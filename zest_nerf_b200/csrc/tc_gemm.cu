@@ -1,0 +1,678 @@
+// Generic-stride fp32 GEMM on the tcgen05 tensor cores: C[I,J] (+)= A[I,K] * B[J,K]^T with fp32 operands in
+// global memory, each split on the fly into a head and a residual (a = a_hi + a_lo) and multiplied as three
+// UMMAs with fp32 accumulation in TMEM:
+//
+//     A*B ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi
+//
+//   engine 1: bf16 head + bf16 residual (16 mantissa bits), one accumulator
+//   engine 2: tf32 head + tf32 residual, both round-to-nearest (22 mantissa bits, twice the tensor-pipe time); the
+//             weight-operand GEMMs (forward, dX) keep the head product and the cross products in two accumulators
+// Measured against fp64 (tests/test_gpu_parity.py), K = 256..347, one accumulator: fp32 SIMT 6e-7, 3 x tf32 2-3.5e-6,
+// 3 x bf16 4-6e-6 of max|C|; unsplit K = 5000: 3.2e-6 / 3.7e-5 / 1.8e-5.  The tensor core's fp32 accumulate TRUNCATES:
+// a bias per chained UMMA that grows linearly with the chain and compounds through the layers of the MLP.  Hence: long
+// reductions are cut into <= 192-UMMA accumulators joined by round-to-nearest atomics, and engine 2 accumulates the
+// small cross products apart from the head product.
+//
+// This is the training path's GEMM (fine_tune.py: forward with saved activations, dX, dW of networks.py:150-221),
+// taking the same GemmArgs / fused epilogue (bias, pre-gate copy, gate, ReLU, accumulate, split-K atomics) as the
+// CUDA-core sgemm_kernel it replaces; the exact-fp32 SIMT kernel stays selectable (zest_set_gemm_engine).
+//
+// One CTA = one 128 x (<=256) output tile, 256 threads, 2 CTAs per SM (96 KB smem, 256 TMEM columns each) so one
+// CTA's epilogue overlaps the other's main loop.  Main loop per K stage (32 k as bf16, 16 k as tf32):
+//   all threads: convert the register-prefetched fp32 operand slab -> hi / lo images in the K-major no-swizzle
+//                UMMA layout (core matrix = 8 rows x 16 B; same layout the MLP kernel uses), then issue the next
+//                stage's global loads (vector loads along whichever dimension is contiguous)
+//   thread 0:    6 UMMAs (2 K steps x 3 products), tcgen05.commit -> the stage's "empty" mbarrier
+// Epilogue: tcgen05.ld 32 columns per warp pass (lane = row), per-warp shared-memory transpose, fused ops, then
+// global accesses in which a warp covers 4 rows x 128 contiguous bytes.
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+
+#include "sgemm.cuh"
+#include "tc_ptx.cuh"
+
+namespace zest {
+namespace {
+
+constexpr int GM = 128, GN = 256;
+constexpr int kThreads = 256;
+// A stage image = 4 K-chunks of 16 bytes per row and per part (hi / lo): 32 k as bf16 (KCH = 8 elements per chunk)
+// or 16 k as tf32 (KCH = 4).  Same bytes either way.
+constexpr uint32_t kAHalf = GM * 4 * 16;               // bytes of one part (hi or lo) of the A stage: 8 KB
+constexpr uint32_t kBHalf = GN * 4 * 16;               // 16 KB
+constexpr uint32_t kStage = 2 * kAHalf + 2 * kBHalf;   // 48 KB
+constexpr int kStages = 2;
+constexpr uint32_t kSmem = kStages * kStage;           // 96 KB -> two CTAs per SM
+constexpr uint32_t kEpiRow = 144;                      // epilogue staging: 32 fp32 columns + 16 B pad per row
+static_assert(8 * 32 * kEpiRow <= kSmem, "epilogue staging must fit in the stage buffers");
+
+__device__ __forceinline__ void gemm_wait(uint32_t bar, uint32_t parity, int tag) {
+  if (ptx::mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!ptx::mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 21)) {  // a protocol bug must not hang the GPU
+      printf("zest tc_gemm: barrier timeout tag=%d block=(%d,%d,%d) thread=%d\n", tag, blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t to_tf32(float a) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
+  return r;
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, tf32 x tf32 -> fp32 (K = 8 per instruction)
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::tf32 instruction descriptor: D = f32, A = B = tf32 (format 2), both K-major, M = 128
+__device__ __forceinline__ uint32_t idesc_tf32(int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// one 16-byte K chunk of one row -> the hi image and the lo image
+//   KCH = 8: 8 fp32 -> 8 bf16 heads + 8 bf16 residuals (a = hi + lo to 2^-18)
+//   KCH = 4: 4 fp32 -> 4 tf32 heads + 4 tf32 residuals (round-to-nearest both: a = hi + lo to 2^-23)
+template <int KCH>
+__device__ __forceinline__ void split_chunk(const float* v, uint32_t (&h)[4], uint32_t (&l)[4]) {
+  if constexpr (KCH == 8) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      h[e] = ptx::pack_bf16(v[2 * e], v[2 * e + 1]);   // element 2e in the low half = lower address
+      l[e] = ptx::pack_bf16(v[2 * e] - ptx::bf16_lo(h[e]), v[2 * e + 1] - ptx::bf16_hi(h[e]));
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      h[e] = to_tf32(v[e]);
+      l[e] = to_tf32(v[e] - __uint_as_float(h[e]));
+    }
+  }
+}
+template <int KCH>
+__device__ __forceinline__ void store_chunk(uint32_t hi_addr, uint32_t lo_addr, const float* v) {
+  uint32_t h[4], l[4];
+  split_chunk<KCH>(v, h, l);
+  ptx::st_smem_v4(hi_addr, h[0], h[1], h[2], h[3]);
+  ptx::st_smem_v4(lo_addr, l[0], l[1], l[2], l[3]);
+}
+
+// ---- operand staging.  R = rows of the stage image (128 for A, 256 for B), NU = units per thread.
+// k-contiguous operand (stride 1 along K): unit = 1 row x 1 chunk.  Lane -> (row = 8 (u / 32) + lane % 8, chunk = lane / 8):
+// the 8 lanes of a quarter-warp store to 8 consecutive rows of one chunk (8 distinct 16-byte bank groups), and a warp load
+// covers 8 rows x the stage's whole K extent.
+template <int KCH, int R, int NU>
+struct StageKC {
+  float v[NU * KCH];
+  __device__ __forceinline__ void fetch(const float* __restrict__ base, int64_t s_row, int64_t rows, int64_t r0, int64_t k0,
+                                        int64_t ke, int rows_used, int tid) {
+#pragma unroll
+    for (int n = 0; n < NU; ++n) {
+      const int u = tid + n * kThreads;
+      const int row = (u >> 5) * 8 + (u & 7), c = (u >> 3) & 3;
+      const int64_t r = r0 + row, k = k0 + c * KCH;
+      const float* p = base + r * s_row + k;
+      float* o = v + n * KCH;
+      const bool in = row < rows_used && r < rows;
+      if (in && k + KCH - 1 < ke && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+        for (int e = 0; e < KCH; e += 4) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(p + e));
+          o[e] = a.x; o[e + 1] = a.y; o[e + 2] = a.z; o[e + 3] = a.w;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < KCH; ++e) o[e] = (in && k + e < ke) ? __ldg(p + e) : 0.f;
+      }
+    }
+  }
+  // the two rows of a 128-row image this thread stages (NU = 2), and the running sums of what it staged for them
+  static __device__ __forceinline__ int row_of(int slot, int tid) { const int u = tid + slot * kThreads; return (u >> 5) * 8 + (u & 7); }
+  __device__ __forceinline__ void rowsums(float& s0, float& s1) const {
+#pragma unroll
+    for (int e = 0; e < KCH; ++e) { s0 += v[e]; s1 += v[(NU > 1 ? KCH : 0) + e]; }
+  }
+  __device__ __forceinline__ void store(uint32_t hi_base, uint32_t lo_base, int rows_used, int tid) const {
+#pragma unroll
+    for (int n = 0; n < NU; ++n) {
+      const int u = tid + n * kThreads;
+      const int row = (u >> 5) * 8 + (u & 7), c = (u >> 3) & 3;
+      if (row >= rows_used) continue;
+      const uint32_t off = (uint32_t)c * (R * 16) + (uint32_t)row * 16;
+      store_chunk<KCH>(hi_base + off, lo_base + off, v + n * KCH);
+    }
+  }
+};
+
+// row-contiguous operand (stride 1 along the output dimension): unit = 2 rows x 1 chunk, one 8-byte load per k; the 32
+// lanes of a load cover 256 contiguous bytes.
+template <int KCH, int R, int NU>
+struct StageRC {
+  float v[NU * 2 * KCH];
+  __device__ __forceinline__ void fetch(const float* __restrict__ base, int64_t s_k, int64_t rows, int64_t r0, int64_t k0,
+                                        int64_t ke, int rows_used, int tid) {
+#pragma unroll
+    for (int n = 0; n < NU; ++n) {
+      const int u = tid + n * kThreads;
+      const int rp = u % (R / 2), c = u / (R / 2);
+      const int64_t r = r0 + 2 * rp, k = k0 + c * KCH;
+      const float* p = base + k * s_k + r;
+      float* o = v + n * 2 * KCH;
+      const bool used = 2 * rp < rows_used;
+      const bool vec = used && r + 1 < rows && (s_k & 1) == 0 && (reinterpret_cast<uintptr_t>(p) & 7) == 0;
+#pragma unroll
+      for (int e = 0; e < KCH; ++e) {
+        if (vec && k + e < ke) {
+          const float2 t = __ldg(reinterpret_cast<const float2*>(p + e * s_k));
+          o[e] = t.x; o[KCH + e] = t.y;
+        } else {
+          const bool kin = used && k + e < ke;
+          o[e] = (kin && r < rows) ? __ldg(p + e * s_k) : 0.f;
+          o[KCH + e] = (kin && r + 1 < rows) ? __ldg(p + e * s_k + 1) : 0.f;
+        }
+      }
+    }
+  }
+  static __device__ __forceinline__ int row_of(int slot, int tid) { return 2 * (tid % (R / 2)) + slot; }
+  __device__ __forceinline__ void rowsums(float& s0, float& s1) const {
+#pragma unroll
+    for (int e = 0; e < KCH; ++e) { s0 += v[e]; s1 += v[KCH + e]; }
+  }
+  __device__ __forceinline__ void store(uint32_t hi_base, uint32_t lo_base, int rows_used, int tid) const {
+    // lanes 4..7 of every quarter-warp store their second row first: the eight 16-byte stores of one shared-memory
+    // wavefront then land in eight distinct 16-byte bank groups
+    const bool swap = (tid >> 2) & 1;
+#pragma unroll
+    for (int n = 0; n < NU; ++n) {
+      const int u = tid + n * kThreads;
+      const int rp = u % (R / 2), c = u / (R / 2);
+      if (2 * rp >= rows_used) continue;
+      const float* o = v + n * 2 * KCH;
+      float first[KCH], second[KCH];
+#pragma unroll
+      for (int e = 0; e < KCH; ++e) { first[e] = swap ? o[KCH + e] : o[e]; second[e] = swap ? o[e] : o[KCH + e]; }
+      const uint32_t off = (uint32_t)c * (R * 16) + (uint32_t)(2 * rp) * 16;
+      const uint32_t o1 = off + (swap ? 16u : 0u), o2 = off + (swap ? 0u : 16u);
+      store_chunk<KCH>(hi_base + o1, lo_base + o1, first);
+      store_chunk<KCH>(hi_base + o2, lo_base + o2, second);
+    }
+  }
+};
+
+// ---- epilogue (8 warps).  Warp w owns TMEM lanes 32 (w % 4) .. +31 (rows) and the 32-column passes w / 4, w / 4 + 2, ...
+// tcgen05.ld gives lane = row; a per-warp shared-memory transpose (the stage buffers are free by now) turns that into
+// lane = (row % 4, 4 consecutive columns) so that every global access of a warp covers 4 rows x 128 contiguous bytes.
+template <bool DUAL = false>
+__device__ __forceinline__ void gemm_epilogue(const GemmArgs& g, uint32_t tmem, uint32_t smem0, int warp, int lane, int64_t i0,
+                                              int j0, int im, int jn, int n_mma, bool atomic, bool first_split) {
+  const int q = warp & 3;
+  const uint32_t stg = smem0 + (uint32_t)warp * (32 * kEpiRow);
+  const int cq = (lane & 7) * 4, rsub = lane >> 3;
+  for (int c0 = (warp >> 2) * 32; c0 < n_mma; c0 += 64) {
+    uint32_t r[32];
+    ptx::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+    if constexpr (DUAL) {   // + the cross-product accumulator
+      uint32_t r2[32];
+      ptx::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)c0, r2);
+      ptx::tc_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+    } else {
+      ptx::tc_wait_ld();
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ptx::st_smem_v4(stg + (uint32_t)lane * kEpiRow + e * 16, r[4 * e], r[4 * e + 1], r[4 * e + 2], r[4 * e + 3]);
+    __syncwarp();
+    const int j = j0 + c0 + cq;                 // this lane's first column
+    const int nv = g.J - j;                     // valid columns among its 4 (<= 0: none)
+    float b4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (g.bias && first_split) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) if (t < nv) b4[t] = __ldg(g.bias + j + t);
+    }
+#pragma unroll 2
+    for (int rr = 0; rr < 32; rr += 4) {
+      const int row = q * 32 + rr + rsub;
+      const uint4 w = ptx::ld_smem_v4(stg + (uint32_t)(rr + rsub) * kEpiRow + cq * 4);
+      if (row >= im || nv <= 0) continue;
+      const int64_t i = i0 + row;
+      float v[4] = {__uint_as_float(w.x) + b4[0], __uint_as_float(w.y) + b4[1], __uint_as_float(w.z) + b4[2], __uint_as_float(w.w) + b4[3]};
+      float* c = g.C + i * g.ldc + j;
+      float* z = g.Z ? g.Z + i * g.ldz + j : nullptr;
+      const float* gt = g.gate ? g.gate + i * g.ldg + j : nullptr;
+      const bool full = nv >= 4;
+      if (g.gb_dZ && j + 3 >= g.gb_col0) {   // fused gate backward (see GemmArgs); columns below gb_col0 fall through to C
+        if (g.accumulate) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) if (t < nv) v[t] += c[t];
+        }
+        const int64_t o = i * g.gb_ld + (j - g.gb_col0);
+        if (full && j >= g.gb_col0 && ((g.gb_ld | (int64_t)(j - g.gb_col0)) & 3) == 0 &&
+            ((reinterpret_cast<uintptr_t>(g.gb_Z) | reinterpret_cast<uintptr_t>(g.gb_G) | reinterpret_cast<uintptr_t>(g.gb_gG) |
+              reinterpret_cast<uintptr_t>(g.gb_dZ)) & 15) == 0) {
+          const float4 zz = __ldg(reinterpret_cast<const float4*>(g.gb_Z + o));
+          const float4 gg = __ldg(reinterpret_cast<const float4*>(g.gb_G + o));
+          float4 acc = *reinterpret_cast<const float4*>(g.gb_gG + o);
+          const float m0 = (zz.x * gg.x > 0.f) ? v[0] : 0.f, m1 = (zz.y * gg.y > 0.f) ? v[1] : 0.f;
+          const float m2 = (zz.z * gg.z > 0.f) ? v[2] : 0.f, m3 = (zz.w * gg.w > 0.f) ? v[3] : 0.f;
+          *reinterpret_cast<float4*>(g.gb_dZ + o) = make_float4(m0 * gg.x, m1 * gg.y, m2 * gg.z, m3 * gg.w);
+          acc.x += m0 * zz.x; acc.y += m1 * zz.y; acc.z += m2 * zz.z; acc.w += m3 * zz.w;
+          *reinterpret_cast<float4*>(g.gb_gG + o) = acc;
+        } else {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (t >= nv) continue;
+            if (j + t < g.gb_col0) { c[t] = v[t]; continue; }     // (v already holds C + acc when accumulating)
+            const float zz = __ldg(g.gb_Z + o + t), gg = __ldg(g.gb_G + o + t);
+            const float m = (zz * gg > 0.f) ? v[t] : 0.f;
+            g.gb_dZ[o + t] = m * gg;
+            g.gb_gG[o + t] += m * zz;
+          }
+        }
+        continue;
+      }
+      if (z) {
+        if (full && (reinterpret_cast<uintptr_t>(z) & 15) == 0) *reinterpret_cast<float4*>(z) = make_float4(v[0], v[1], v[2], v[3]);
+        else {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) if (t < nv) z[t] = v[t];
+        }
+      }
+      if (gt) {
+        if (full && (reinterpret_cast<uintptr_t>(gt) & 15) == 0) {
+          const float4 gg = __ldg(reinterpret_cast<const float4*>(gt));
+          v[0] *= gg.x; v[1] *= gg.y; v[2] *= gg.z; v[3] *= gg.w;
+        } else {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) if (t < nv) v[t] *= __ldg(gt + t);
+        }
+      }
+      if (g.relu) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) v[t] = fmaxf(v[t], 0.f);
+      }
+      if (atomic) {
+        if (full && (reinterpret_cast<uintptr_t>(c) & 15) == 0) atomicAdd(reinterpret_cast<float4*>(c), make_float4(v[0], v[1], v[2], v[3]));
+        else {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) if (t < nv) atomicAdd(c + t, v[t]);
+        }
+      } else if (full && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
+        if (g.accumulate) {
+          const float4 old = *reinterpret_cast<const float4*>(c);
+          v[0] += old.x; v[1] += old.y; v[2] += old.z; v[3] += old.w;
+        }
+        *reinterpret_cast<float4*>(c) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) if (t < nv) c[t] = g.accumulate ? c[t] + v[t] : v[t];
+      }
+    }
+    __syncwarp();   // the next pass overwrites the staging rows
+  }
+}
+
+template <int KCH, bool KC, int R>
+struct StagePick;
+template <int KCH, int R>
+struct StagePick<KCH, true, R> { using type = StageKC<KCH, R, R * 4 / kThreads>; };
+template <int KCH, int R>
+struct StagePick<KCH, false, R> { using type = StageRC<KCH, R, R * 2 / kThreads>; };
+
+// KCH = 8: three bf16 UMMAs per product (K = 32 per stage); KCH = 4: three tf32 UMMAs per product (K = 16 per stage)
+template <int KCH, bool AKC, bool BKC>
+__global__ void __launch_bounds__(kThreads, 2) tc_gemm_kernel(GemmArgs g, int64_t kper) {
+  constexpr int GK = 4 * KCH;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t empty_bar[kStages];
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t i0 = (int64_t)blockIdx.x * GM;
+  const int j0 = (int)blockIdx.y * GN;
+  const int64_t kb = (int64_t)blockIdx.z * kper;
+  const int64_t ke = (kb + kper < g.K) ? kb + kper : g.K;
+  if (kb >= ke) return;                       // empty K slice of a split (nothing to add); uniform for the CTA
+  const int jn = (g.J - j0 < GN) ? g.J - j0 : GN;          // valid columns of this tile
+  const int n_mma = (jn + 15) & ~15;                        // UMMA N
+  const int im = (g.I - i0 < GM) ? (int)(g.I - i0) : GM;    // valid rows of this tile
+  const int nkt = (int)((ke - kb + GK - 1) / GK);
+
+  const uint32_t smem0 = ptx::smem_u32(smem_raw);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) { ptx::tmem_alloc(ptx::smem_u32(&s_tmem), 256); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  typename StagePick<KCH, AKC, GM>::type ra;
+  typename StagePick<KCH, BKC, GN>::type rb;
+  const int64_t a_s = AKC ? g.sa_i : g.sa_k, b_s = BKC ? g.sb_j : g.sb_k;
+  ra.fetch(g.A, a_s, g.I, i0, kb, ke, GM, tid);            // all 128 A rows are read by the MMA: zero-fill beyond I
+  rb.fetch(g.B, b_s, g.J, j0, kb, ke, n_mma, tid);
+  const uint32_t idesc = KCH == 8 ? ptx::idesc_bf16(n_mma) : idesc_tf32(n_mma);
+  const bool want_rowsum = g.rowsum != nullptr && blockIdx.y == 0;   // bias gradient: row sums of A (exact fp32 adds)
+  float rsum0 = 0.f, rsum1 = 0.f;
+
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int s = kt & 1;
+    const uint32_t slot = smem0 + (uint32_t)s * kStage;
+    if (kt >= kStages) gemm_wait(ptx::smem_u32(&empty_bar[s]), (uint32_t)((kt >> 1) - 1) & 1u, 1);   // UMMAs of stage kt-2 retired
+    if (want_rowsum) ra.rowsums(rsum0, rsum1);
+    ra.store(slot, slot + kAHalf, GM, tid);
+    rb.store(slot + 2 * kAHalf, slot + 2 * kAHalf + kBHalf, n_mma, tid);
+    if (kt + 1 < nkt) {
+      const int64_t k0 = kb + (int64_t)(kt + 1) * GK;
+      ra.fetch(g.A, a_s, g.I, i0, k0, ke, GM, tid);
+      rb.fetch(g.B, b_s, g.J, j0, k0, ke, n_mma, tid);
+    }
+    ptx::fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {   // one UMMA K step = two 16-byte chunks
+        const uint64_t a_hi = ptx::smem_desc(slot + ks * (2 * GM * 16), GM * 16, 128);
+        const uint64_t a_lo = ptx::smem_desc(slot + kAHalf + ks * (2 * GM * 16), GM * 16, 128);
+        const uint64_t b_hi = ptx::smem_desc(slot + 2 * kAHalf + ks * (2 * GN * 16), GN * 16, 128);
+        const uint64_t b_lo = ptx::smem_desc(slot + 2 * kAHalf + kBHalf + ks * (2 * GN * 16), GN * 16, 128);
+        const uint32_t acc0 = (kt > 0 || ks > 0) ? 1u : 0u;
+        if constexpr (KCH == 8) {
+          ptx::mma_bf16_ss(tmem, a_lo, b_hi, idesc, acc0);
+          ptx::mma_bf16_ss(tmem, a_hi, b_lo, idesc, 1u);
+          ptx::mma_bf16_ss(tmem, a_hi, b_hi, idesc, 1u);
+        } else {
+          mma_tf32_ss(tmem, a_lo, b_hi, idesc, acc0);
+          mma_tf32_ss(tmem, a_hi, b_lo, idesc, 1u);
+          mma_tf32_ss(tmem, a_hi, b_hi, idesc, 1u);
+        }
+      }
+      ptx::mma_commit(ptx::smem_u32(&empty_bar[s]));
+    }
+  }
+  if (want_rowsum) {   // 4 threads (the 4 K chunks) hold partial sums of each row
+    const int r0 = decltype(ra)::row_of(0, tid), r1 = decltype(ra)::row_of(1, tid);
+    if (r0 < im) atomicAdd(g.rowsum + i0 + r0, rsum0);
+    if (r1 < im) atomicAdd(g.rowsum + i0 + r1, rsum1);
+  }
+  // the last commit covers every UMMA issued before it
+  gemm_wait(ptx::smem_u32(&empty_bar[(nkt - 1) & 1]), (uint32_t)((nkt - 1) >> 1) & 1u, 2);
+  ptx::tc_fence_after();
+
+  gemm_epilogue(g, tmem, smem0, warp, lane, i0, j0, im, jn, n_mma, gridDim.z > 1, blockIdx.z == 0);
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 256); }
+}
+
+// ---- weights as the B operand (forward, dX): packed once per call into the stage images (hi | lo per 256-row tile and
+// K stage, zero padded) by a tiny kernel, then streamed by the TMA engine: no registers, no thread work, one stage ahead.
+template <int KCH>
+__global__ void gemm_pack_b_kernel(const float* __restrict__ B, int64_t sb_j, int64_t sb_k, int J, int64_t K, int nst, int64_t total,
+                                   uint8_t* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int row = (int)(idx & 255), c = (int)((idx >> 8) & 3);
+  const int64_t sidx = idx >> 10;                  // tile * nst + stage
+  const int st = (int)(sidx % nst);
+  const int64_t j = (sidx / nst) * GN + row, k = (int64_t)st * (4 * KCH) + c * KCH;
+  float v[KCH];
+#pragma unroll
+  for (int e = 0; e < KCH; ++e) v[e] = (j < J && k + e < K) ? __ldg(B + j * sb_j + (k + e) * sb_k) : 0.f;
+  uint32_t h[4], l[4];
+  split_chunk<KCH>(v, h, l);
+  uint8_t* dst = out + sidx * (2 * kBHalf) + (size_t)c * (GN * 16) + (size_t)row * 16;
+  *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(dst + kBHalf) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+constexpr int kWorkers = 256;              // warps 0..7 stage A and run the epilogue; warp 8 drives the TMA and the UMMAs
+
+// DUAL = false: one accumulator, 2 stages, 2 CTAs per SM (one CTA's epilogue overlaps the other's main loop).
+// DUAL = true:  the head product a_hi*b_hi accumulates in TMEM columns [0,256), the two cross products in [256,512), added
+//               in the epilogue in fp32.  The tensor core's fp32 accumulate truncates, a bias that compounds layer by layer
+//               through the MLP's forward / dX chain; the main accumulator now sees a third of the UMMAs and the cross
+//               accumulator is 2^-11 of its magnitude.  All of TMEM -> one CTA per SM, 4 stages.
+template <int KCH, bool AKC, bool DUAL>
+__global__ void __launch_bounds__(kWorkers + 32, DUAL ? 1 : 2) tc_gemm_packed_kernel(GemmArgs g, const uint8_t* __restrict__ bpack) {
+  constexpr int GK = 4 * KCH;
+  constexpr int NS = DUAL ? 4 : kStages;      // smem stages (power of two)
+  constexpr int PD = NS - 1;                  // the TMA runs this many stages ahead of the UMMAs
+  constexpr uint32_t kCols = DUAL ? 512 : 256;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t empty_bar[NS], full_bar[NS], aready_bar[NS];
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t i0 = (int64_t)blockIdx.x * GM;
+  const int j0 = (int)blockIdx.y * GN;
+  const int jn = (g.J - j0 < GN) ? g.J - j0 : GN;
+  const int n_mma = (jn + 15) & ~15;
+  const int im = (g.I - i0 < GM) ? (int)(g.I - i0) : GM;
+  const int nkt = (int)((g.K + GK - 1) / GK);
+
+  const uint32_t smem0 = ptx::smem_u32(smem_raw);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&aready_bar[s]), kWorkers / 32);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) { ptx::tmem_alloc(ptx::smem_u32(&s_tmem), kCols); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      const uint8_t* src = bpack + (size_t)blockIdx.y * nkt * (2 * kBHalf);
+      const uint32_t idesc = KCH == 8 ? ptx::idesc_bf16(n_mma) : idesc_tf32(n_mma);
+      auto load_b = [&](int t) {   // weights of stage t -> slot t % NS
+        const uint32_t slot = smem0 + (uint32_t)(t & (NS - 1)) * kStage;
+        const uint32_t bar = ptx::smem_u32(&full_bar[t & (NS - 1)]);
+        ptx::mbar_arrive_expect_tx(bar, 2 * kBHalf);
+        ptx::bulk_g2s(slot + 2 * kAHalf, src + (size_t)t * (2 * kBHalf), 2 * kBHalf, bar);
+      };
+      for (int t = 0; t < PD && t < nkt; ++t) load_b(t);
+      const uint32_t cross = DUAL ? tmem + 256 : tmem;
+      for (int kt = 0; kt < nkt; ++kt) {
+        const int s = kt & (NS - 1);
+        const uint32_t par = (uint32_t)(kt / NS) & 1u;
+        const uint32_t slot = smem0 + (uint32_t)s * kStage;
+        gemm_wait(ptx::smem_u32(&aready_bar[s]), par, 4);
+        gemm_wait(ptx::smem_u32(&full_bar[s]), par, 5);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint64_t a_hi = ptx::smem_desc(slot + ks * (2 * GM * 16), GM * 16, 128);
+          const uint64_t a_lo = ptx::smem_desc(slot + kAHalf + ks * (2 * GM * 16), GM * 16, 128);
+          const uint64_t b_hi = ptx::smem_desc(slot + 2 * kAHalf + ks * (2 * GN * 16), GN * 16, 128);
+          const uint64_t b_lo = ptx::smem_desc(slot + 2 * kAHalf + kBHalf + ks * (2 * GN * 16), GN * 16, 128);
+          const uint32_t acc0 = (kt > 0 || ks > 0) ? 1u : 0u;
+          if constexpr (KCH == 8) {
+            ptx::mma_bf16_ss(cross, a_lo, b_hi, idesc, acc0);
+            ptx::mma_bf16_ss(cross, a_hi, b_lo, idesc, 1u);
+            ptx::mma_bf16_ss(tmem, a_hi, b_hi, idesc, DUAL ? acc0 : 1u);
+          } else {
+            mma_tf32_ss(cross, a_lo, b_hi, idesc, acc0);
+            mma_tf32_ss(cross, a_hi, b_lo, idesc, 1u);
+            mma_tf32_ss(tmem, a_hi, b_hi, idesc, DUAL ? acc0 : 1u);
+          }
+        }
+        ptx::mma_commit(ptx::smem_u32(&empty_bar[s]));
+        if (kt + PD < nkt) {   // stage kt + PD reuses the slot of stage kt - 1: free once those UMMAs have retired
+          if (kt >= 1) gemm_wait(ptx::smem_u32(&empty_bar[(kt - 1) & (NS - 1)]), (uint32_t)((kt - 1) / NS) & 1u, 3);
+          load_b(kt + PD);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // workers: A two stages ahead in registers (two static register sets), no CTA-wide barrier in the loop
+    typename StagePick<KCH, AKC, GM>::type r0, r1;
+    const int64_t a_s = AKC ? g.sa_i : g.sa_k;
+    r0.fetch(g.A, a_s, g.I, i0, 0, g.K, GM, tid);
+    if (nkt > 1) r1.fetch(g.A, a_s, g.I, i0, GK, g.K, GM, tid);
+    auto step = [&](auto& r, int kt) {
+      const int s = kt & (NS - 1);
+      const uint32_t slot = smem0 + (uint32_t)s * kStage;
+      if (kt >= NS) gemm_wait(ptx::smem_u32(&empty_bar[s]), (uint32_t)(kt / NS - 1) & 1u, 1);
+      r.store(slot, slot + kAHalf, GM, tid);
+      if (kt + 2 < nkt) r.fetch(g.A, a_s, g.I, i0, (int64_t)(kt + 2) * GK, g.K, GM, tid);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&aready_bar[s]));
+    };
+    for (int kt = 0; kt < nkt; kt += 2) {
+      step(r0, kt);
+      if (kt + 1 < nkt) step(r1, kt + 1);
+    }
+    gemm_wait(ptx::smem_u32(&empty_bar[(nkt - 1) & (NS - 1)]), (uint32_t)((nkt - 1) / NS) & 1u, 2);
+    ptx::tc_fence_after();
+    gemm_epilogue<DUAL>(g, tmem, smem0, warp, lane, i0, j0, im, jn, n_mma, false, true);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, kCols); }
+}
+
+template <int KCH, bool AKC, bool DUAL>
+int launch_packed_variant(const GemmArgs& a, dim3 grid, cudaStream_t st) {
+  constexpr uint32_t smem = (DUAL ? 4 : kStages) * kStage;
+  static bool configured = false;
+  if (!configured) {
+    ZEST_CUDA(cudaFuncSetAttribute(tc_gemm_packed_kernel<KCH, AKC, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  tc_gemm_packed_kernel<KCH, AKC, DUAL><<<grid, kWorkers + 32, smem, st>>>(a, (const uint8_t*)a.b_scratch);
+  ZEST_LAUNCH_CHECK();
+  return ZEST_OK;
+}
+
+template <int KCH, bool DUAL>
+int launch_packed(const GemmArgs& a, dim3 grid, cudaStream_t st) {
+  constexpr int GK = 4 * KCH;
+  const int nst = (int)((a.K + GK - 1) / GK);
+  const int64_t total = (int64_t)grid.y * nst * 1024;
+  gemm_pack_b_kernel<KCH><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a.B, a.sb_j, a.sb_k, a.J, a.K, nst, total, (uint8_t*)a.b_scratch);
+  ZEST_LAUNCH_CHECK();
+  return a.sa_k == 1 ? launch_packed_variant<KCH, true, DUAL>(a, grid, st) : launch_packed_variant<KCH, false, DUAL>(a, grid, st);
+}
+
+template <int KCH, bool AKC, bool BKC>
+int launch_variant(const GemmArgs& a, dim3 grid, int64_t kper, cudaStream_t st) {
+  static bool configured = false;   // per instantiation
+  if (!configured) {
+    ZEST_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<KCH, AKC, BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    configured = true;
+  }
+  tc_gemm_kernel<KCH, AKC, BKC><<<grid, kThreads, kSmem, st>>>(a, kper);
+  ZEST_LAUNCH_CHECK();
+  return ZEST_OK;
+}
+template <int KCH>
+int launch_prec(const GemmArgs& a, dim3 grid, int64_t kper, cudaStream_t st) {
+  const bool akc = a.sa_k == 1, bkc = a.sb_k == 1;
+  if (akc && bkc) return launch_variant<KCH, true, true>(a, grid, kper, st);
+  if (akc && !bkc) return launch_variant<KCH, true, false>(a, grid, kper, st);
+  if (!akc && bkc) return launch_variant<KCH, false, true>(a, grid, kper, st);
+  return launch_variant<KCH, false, false>(a, grid, kper, st);
+}
+
+std::atomic<int> g_engine{-1};
+
+}  // namespace
+
+// 0 = exact-fp32 CUDA cores, 1 = tcgen05 3 x bf16 (fastest), 2 = tcgen05 3 x tf32 with split accumulators (fp32-grade, default)
+int gemm_engine() {
+  int e = g_engine.load(std::memory_order_relaxed);
+  if (e < 0) {
+    const char* s = getenv("ZEST_GEMM");
+    e = 2;
+    if (s && (!strcmp(s, "simt") || !strcmp(s, "0"))) e = 0;
+    else if (s && (!strcmp(s, "bf16x3") || !strcmp(s, "1"))) e = 1;
+    g_engine.store(e, std::memory_order_relaxed);
+  }
+  return e;
+}
+void set_gemm_engine(int e) { g_engine.store(e < 0 ? 0 : (e > 2 ? 2 : e), std::memory_order_relaxed); }
+
+bool gemm_tc_supported(const GemmArgs& a) {
+  return (a.sa_k == 1 || a.sa_i == 1) && (a.sb_k == 1 || a.sb_j == 1) && a.K >= 1 && a.J >= 1;
+}
+
+int launch_gemm_tc(const GemmArgs& a0, int engine, cudaStream_t st) {
+  GemmArgs a = a0;
+  ZEST_CHECK_ARG(gemm_tc_supported(a), "tc gemm: operands need unit stride along one dimension");
+  ZEST_CHECK_ARG(engine == 1 || engine == 2, "tc gemm: engine must be 1 (3 x bf16) or 2 (3 x tf32)");
+  if (a.I == 0) return ZEST_OK;
+  // engine 2 keeps the long split-K reductions (dW) on the bf16 split: half the UMMAs per accumulator (less truncation
+  // bias, measured) and they are leaves of the graph - nothing compounds through them
+  const bool bf16 = engine == 1 || a.splits > 1;
+  const int GK = bf16 ? 32 : 16;
+  const int64_t ti = (a.I + GM - 1) / GM, tj = (a.J + GN - 1) / GN;
+  ZEST_CHECK_ARG(ti < (1ll << 31) && tj < 65536, "tc gemm: shape too large for one launch");
+  int64_t splits = 1;
+  if (a.splits > 1) {   // split-K: the caller only says "reduce over a long K"; fill the machine (2 CTAs / SM)
+    // and keep one TMEM accumulator to <= 192 UMMAs: the tensor core's fp32 accumulate truncates, a bias that grows
+    // linearly with the number of UMMAs chained into one accumulator; the cross-CTA atomics round to nearest
+    splits = (2 * (int64_t)num_sms() + ti * tj - 1) / (ti * tj);
+    const int64_t k_cta_max = 32 * GK, min_splits = (a.K + k_cta_max - 1) / k_cta_max;
+    if (splits < min_splits) splits = min_splits;
+    const int64_t max_splits = (a.K + 255) / 256;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    a.accumulate = 1;
+  }
+  int64_t kper = (a.K + splits - 1) / splits;
+  kper = (kper + GK - 1) / GK * GK;
+  splits = (a.K + kper - 1) / kper;
+  ZEST_CHECK_ARG(splits == 1 || (!a.Z && !a.gate && !a.relu && !a.gb_dZ), "tc gemm: split-K cannot fuse a non-linear epilogue");
+  dim3 grid((unsigned)ti, (unsigned)tj, (unsigned)splits);
+  if (a.b_scratch && splits == 1 && ti >= 8 && !a.rowsum) {   // B is a small matrix re-read by every row tile (weights): pack + TMA
+    const int64_t nst = (a.K + GK - 1) / GK;
+    if (tj * nst * (int64_t)(2 * kBHalf) <= a.b_scratch_bytes)
+      return engine == 1 ? launch_packed<8, false>(a, grid, st) : launch_packed<4, true>(a, grid, st);
+  }
+  return bf16 ? launch_prec<8>(a, grid, kper, st) : launch_prec<4>(a, grid, kper, st);
+}
+
+}  // namespace zest
+
+using namespace zest;
+
+extern "C" int zest_set_gemm_engine(int engine) {
+  const int prev = gemm_engine();
+  set_gemm_engine(engine);
+  return prev;
+}
+
+extern "C" int zest_gemm_f32(const float* A, int64_t sa_i, int64_t sa_k, const float* B, int64_t sb_j, int64_t sb_k, float* C,
+                             int64_t ldc, int64_t I, int J, int64_t K, const float* bias, int accumulate, int splits,
+                             int engine, void* b_scratch, int64_t b_scratch_bytes, void* stream) {
+  ZEST_CHECK_ARG(A && B && C && I >= 0 && J > 0 && K > 0 && splits >= 1, "zest_gemm_f32: bad arguments");
+  ZEST_CHECK_ARG(engine >= 0 && engine <= 2, "zest_gemm_f32: engine must be 0, 1 or 2");
+  GemmArgs a{};
+  a.A = A; a.sa_i = sa_i; a.sa_k = sa_k;
+  a.B = B; a.sb_j = sb_j; a.sb_k = sb_k;
+  a.C = C; a.ldc = ldc; a.I = I; a.J = J; a.K = K;
+  a.bias = bias; a.accumulate = accumulate; a.splits = splits;
+  a.b_scratch = b_scratch; a.b_scratch_bytes = b_scratch ? b_scratch_bytes : 0;
+  if (engine >= 1) return launch_gemm_tc(a, engine, (cudaStream_t)stream);
+  return launch_gemm_simt(a, (cudaStream_t)stream);
+}

@@ -449,7 +449,14 @@ class MlpFn(torch.autograd.Function):
         pk = ctx.pk
         graw = _f32c(graw, "graw")
         gx = torch.zeros_like(x) if ctx.need_x else None
-        gps = [torch.zeros(s, device=x.device, dtype=torch.float32) for s in ctx.pshapes]
+        # one zero-filled allocation for every parameter gradient (the library accumulates into them), 16-byte aligned views
+        import math
+        sizes = [(math.prod(s) + 3) // 4 * 4 for s in ctx.pshapes]
+        flat = torch.zeros((sum(sizes),), device=x.device, dtype=torch.float32)
+        gps, off = [], 0
+        for shp, n in zip(ctx.pshapes, sizes):
+            gps.append(flat[off:off + math.prod(shp)].view(shp))
+            off += n
         arr = (C.c_void_p * len(gps))(*[g.data_ptr() for g in gps])
         _lib.check(_lib.load().zest_mlp_bwd_f32(pk.handle, _ptr(x), x.shape[1], x.shape[0], _ptr(graw), _ptr(ctx.ws),
                                                 _ptr(gx), arr, len(gps), _stream()), "zest_mlp_bwd_f32")
