@@ -41,6 +41,11 @@ CONFIGS = {
     # (strong scaling), volumes / views broadcast per frame with NCCL, per-rank slabs all-gathered
     "cfg4": dict(H=288, W=512, V=3, dynamic=True, Ht=1080, Wt=1920, desc="1080p novel-view frames (wander path), sources 288x512, "
                  "V=3, static+dynamic volumes, each frame ray-sharded across the ranks, per-frame NCCL volume broadcast"),
+    # BASELINE config 5: fine_tune.py step - forward + backward through gather / encode / MLP / composite for a 4096-ray batch
+    # of random pixels with stratified jitter (train mode: 1 static + 3 dynamic network passes), gradients of both volumes
+    # and every MLP parameter.  Timed per GEMM engine of the fp32 MLP path (include/zest_b200.h: zest_set_gemm_engine).
+    "cfg5": dict(H=288, W=512, V=3, dynamic=True, desc="fine-tune step (fwd + bwd), 4096-ray batches of random pixels + stratified "
+                 "jitter, NSFF 288x512 sources, V=3, static+dynamic volumes, train mode"),
 }
 S = 128
 
@@ -221,6 +226,151 @@ def run_sharded_frames(args):
         dist.destroy_process_group()
 
 
+def fine_tune_stage(sc, dev, lib, H, W, steps=4, warmup=2, engines=(2, 1), rays=4096):
+    """BASELINE config 5 on the CUDA training path: ms per fwd+bwd step of a `rays`-ray batch for each GEMM engine.
+    Loss = fixed random projection of every differentiable output (weights resident on the device); CUDA-event time."""
+    import torch
+    from zest_nerf_b200 import rays as zrays
+    from zest_nerf_b200.renderer import rendering
+    g = torch.Generator().manual_seed(5)
+    lin = torch.randperm(H * W, generator=g)[:rays].sort().values
+    t_rand = torch.rand((rays, S), generator=g)
+    cpu = lambda t: t.detach().cpu()
+    pts, rdir, ndc, z = zrays.build_rays_val(H, W, cpu(sc.w2cs), cpu(sc.c2ws), cpu(sc.intrinsics), cpu(sc.near_fars), n_samples=S,
+                                             pad=24, pixels=((lin // W).float(), (lin % W).float()), t_rand=t_rand)
+    d = [t.to(dev) for t in (pts, ndc, z, rdir)]
+    vs, vd = sc.vol_static, sc.vol_dynamic
+    sc.vol_static = vs.detach().clone().requires_grad_(True)
+    sc.vol_dynamic = vd.detach().clone().requires_grad_(True)
+    mode = dict(val=False, chain_bwd=False, chain_5frames=False, raw_noise_std=0)
+    params = [p for net in (sc.net_static, sc.net_dynamic) for p in net.parameters()]
+    wts = {}
+
+    def one_step():
+        for p in params:
+            p.grad = None
+        sc.vol_static.grad = sc.vol_dynamic.grad = None
+        ret = rendering(sc.args, *d, **{**sc.render_kwargs(), **mode})
+        loss = 0.0
+        for k, v in ret.items():
+            if v is None or not v.requires_grad:
+                continue
+            if k not in wts:
+                wts[k] = torch.randn(v.shape, device=dev) / v.numel() ** 0.5
+            loss = loss + (v * wts[k]).sum()
+        loss.backward()
+
+    out = {}
+    try:
+        for engine in engines:
+            prev = lib.zest_set_gemm_engine(engine)
+            try:
+                for _ in range(warmup):
+                    one_step()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                l0 = lib.zest_launch_count()
+                torch.cuda.synchronize(); e0.record()
+                for _ in range(steps):
+                    one_step()
+                e1.record(); torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / steps
+                out[engine] = {"ms_per_step": ms, "rays_per_s": rays / ms * 1e3, "gpu_launches_per_step": (lib.zest_launch_count() - l0) // steps}
+            finally:
+                lib.zest_set_gemm_engine(prev)
+    finally:
+        sc.vol_static, sc.vol_dynamic = vs, vd
+        for p in params:
+            p.grad = None
+    return out
+
+
+FT_ENGINE_NAMES = {0: "fp32 CUDA cores (sgemm)", 1: "tcgen05 3 x bf16, one accumulator", 2: "tcgen05 3 x tf32, split accumulators (default)"}
+
+
+def fine_tune_report(res, V, pk, rays=4096):
+    """rays/s + position against SURVEY 8d's cfg5 roofline (bf16 tensor peak; fwd + bwd = 3 x the forward MACs of 1 static + 3
+    dynamic passes).  The fp32-grade engines spend 3 UMMAs per product (6 bf16-equivalents with tf32), so their own tensor
+    ceiling is 1/3 (3 x bf16) or 1/6 (3 x tf32) of that roofline; layer-by-layer fp32 activations are HBM traffic on top."""
+    ms_s, ms_d = macs_per_sample(V, True)
+    flop_per_ray = 3 * 2.0 * (ms_s + 3 * ms_d) * S
+    peak = pk["bf16_tflops_sustained"]
+    rep = {"rays_per_step": rays, "flop_per_ray": flop_per_ray, "roofline_rays_per_s": peak * 1e12 / flop_per_ray, "engines": {}}
+    for e, r in res.items():
+        rep["engines"][FT_ENGINE_NAMES[e]] = {"ms_per_step": round(r["ms_per_step"], 2), "rays_per_s": round(r["rays_per_s"], 1),
+                                              "algorithmic_tflops": round(r["rays_per_s"] * flop_per_ray / 1e12, 1),
+                                              "frac_of_bf16_tensor_roofline": round(r["rays_per_s"] * flop_per_ray / 1e12 / peak, 4),
+                                              "gpu_launches_per_step": int(r["gpu_launches_per_step"])}
+    return rep
+
+
+def run_fine_tune(args):
+    """--config cfg5: one JSON line for the fine-tune step (single GPU; data-parallel replicas only)."""
+    import torch
+    import __graft_entry__ as ge
+    if not os.path.exists(ge.LIB):
+        ge.build()
+    from zest_nerf_b200 import _lib
+    from zest_nerf_b200.synthetic import make_scene
+    c = CONFIGS["cfg5"]
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    lib = _lib.load()
+    sc = make_scene(H=c["H"], W=c["W"], V=c["V"], pad=24, D=128, dynamic=True, seed=0)
+    sc.to(dev)
+    pk, pk_src = peaks()
+    res = fine_tune_stage(sc, dev, lib, c["H"], c["W"], steps=args.steps, warmup=max(args.warmup, 3), engines=(2, 1, 0))
+    rep = fine_tune_report(res, c["V"], pk)
+    best = res[2]
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_fine_tune(256)
+    line = {"metric": "rays_per_sec_128_samples_fwd_bwd", "value": best["rays_per_s"], "unit": "rays/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": best["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (3 x tf32 UMMAs per product, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": "cfg5: " + c["desc"], "rays_per_step": 4096, "samples_per_ray": S,
+                       "l2": "per-step working set (saved fp32 activations of 4 network passes, ~20 GB) >> L2", "parallelism": "1 GPU"},
+            "gpu_launches": int(best["gpu_launches_per_step"]) * args.steps,
+            "roofline": {"bound": "tensor", "achieved": rep["engines"][FT_ENGINE_NAMES[2]]["algorithmic_tflops"], "peak": pk["bf16_tflops_sustained"],
+                         "unit": "TFLOP/s", "frac": rep["engines"][FT_ENGINE_NAMES[2]]["frac_of_bf16_tensor_roofline"], "traffic": None,
+                         "peak_source": "bf16_tflops_sustained, " + pk_src,
+                         "note": "algorithmic fwd+bwd FLOPs against the bf16 tensor peak (SURVEY 8d cfg5); the default engine issues 3 tf32 "
+                                 "UMMAs per product, so its own tensor ceiling is 1/6 of this peak"},
+            "fine_tune": rep, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_fine_tune(n_rays):
+    """The oracle's autograd fwd+bwd of the same step on the host cores (bounded sample)."""
+    import torch
+    from oracle import zest_oracle as zo
+    from zest_nerf_b200 import rays as zrays
+    from zest_nerf_b200.synthetic import make_scene
+    c = CONFIGS["cfg5"]
+    H, W = c["H"], c["W"]
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sc = make_scene(H=H, W=W, V=c["V"], pad=24, D=128, dynamic=True, seed=0)
+    g = torch.Generator().manual_seed(5)
+    lin = torch.randperm(H * W, generator=g)[:n_rays].sort().values
+    t_rand = torch.rand((n_rays, S), generator=g)
+    pts, rdir, ndc, z = zrays.build_rays_val(H, W, sc.w2cs, sc.c2ws, sc.intrinsics, sc.near_fars, n_samples=S, pad=24,
+                                             pixels=((lin // W).float(), (lin % W).float()), t_rand=t_rand)
+    sc.vol_static.requires_grad_(True); sc.vol_dynamic.requires_grad_(True)
+    mode = dict(val=False, chain_bwd=False, chain_5frames=False, raw_noise_std=0)
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        ret = zo.rendering(sc.args, pts, ndc, z, rdir, **{**sc.render_kwargs(), **mode})
+        loss = sum((v ** 2).mean() for v in ret.values() if v is not None and v.requires_grad)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": n_rays / best, "unit": "rays/s", "cores": threads, "kind": "port",
+            "sample": f"{n_rays}-ray batch, oracle autograd fwd+bwd, best of 2"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -259,11 +409,14 @@ def main():
     ap.add_argument("--mlp", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fine-tune", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     if args.config == "cfg4":
         return run_sharded_frames(args)
+    if args.config == "cfg5":
+        return run_fine_tune(args)
     args.warmup = max(args.warmup, 3)
 
     import torch
@@ -488,6 +641,11 @@ def main():
                   "achieved_gbs": g_bytes / g_ms / 1e6, "peak_gbs": pk["hbm_gbs"], "frac": g_bytes / g_ms / 1e6 / pk["hbm_gbs"],
                   "algorithmic_bytes_per_frame": g_bytes, "note": "volumes (165 MiB) and views are L2-resident: most corner reads never reach HBM"}
 
+    # BASELINE config 5 next to the headline: the fine-tune step (fwd + bwd) of a 4096-ray batch on the same scene
+    ft = None
+    if rank == 0 and world == 1 and c["dynamic"] and not args.no_fine_tune:
+        ft = fine_tune_report(fine_tune_stage(sc, dev, lib, H, W, steps=3, warmup=2, engines=(2, 1)), V, pk)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, sample = cpu_reference(args.config, 4096, 2)
@@ -502,7 +660,7 @@ def main():
                            "l2": "256 MiB buffer written between timed steps (L2 flush); per-step working set 3.6 GB > L2",
                            "parallelism": f"ray-sharded x{world}, one NCCL frame broadcast per step" if world > 1 else "1 GPU"},
                 "steps_ms": [round(x, 3) for x in ms], "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
-                "gather_stage": gstage, "next_rows": {"f1_ray_builder": f1}}
+                "gather_stage": gstage, "fine_tune": ft, "next_rows": {"f1_ray_builder": f1}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
