@@ -210,7 +210,7 @@ struct StageRC {
 // ---- epilogue (8 warps).  Warp w owns TMEM lanes 32 (w % 4) .. +31 (rows) and the 32-column passes w / 4, w / 4 + 2, ...
 // tcgen05.ld gives lane = row; a per-warp shared-memory transpose (the stage buffers are free by now) turns that into
 // lane = (row % 4, 4 consecutive columns) so that every global access of a warp covers 4 rows x 128 contiguous bytes.
-template <bool DUAL = false>
+template <int CROSS = 0>   // CROSS > 0: add the cross-product accumulator that lives CROSS columns above the main one
 __device__ __forceinline__ void gemm_epilogue(const GemmArgs& g, uint32_t tmem, uint32_t smem0, int warp, int lane, int64_t i0,
                                               int j0, int im, int jn, int n_mma, bool atomic, bool first_split) {
   const int q = warp & 3;
@@ -219,9 +219,9 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs& g, uint32_t tmem, 
   for (int c0 = (warp >> 2) * 32; c0 < n_mma; c0 += 64) {
     uint32_t r[32];
     ptx::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-    if constexpr (DUAL) {   // + the cross-product accumulator
+    if constexpr (CROSS > 0) {
       uint32_t r2[32];
-      ptx::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)c0, r2);
+      ptx::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)CROSS + (uint32_t)c0, r2);
       ptx::tc_wait_ld();
 #pragma unroll
       for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
@@ -417,47 +417,51 @@ __global__ void __launch_bounds__(kThreads, 2) tc_gemm_kernel(GemmArgs g, int64_
   if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 256); }
 }
 
-// ---- weights as the B operand (forward, dX): packed once per call into the stage images (hi | lo per 256-row tile and
-// K stage, zero padded) by a tiny kernel, then streamed by the TMA engine: no registers, no thread work, one stage ahead.
-template <int KCH>
+// ---- weights as the B operand (forward, dX): packed once per call into the stage images (hi | lo per TN-row tile and
+// K stage, zero padded) by a tiny kernel, then streamed by the TMA engine: no registers, no thread work, stages ahead.
+template <int KCH, int TN>
 __global__ void gemm_pack_b_kernel(const float* __restrict__ B, int64_t sb_j, int64_t sb_k, int J, int64_t K, int nst, int64_t total,
                                    uint8_t* __restrict__ out) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int row = (int)(idx & 255), c = (int)((idx >> 8) & 3);
-  const int64_t sidx = idx >> 10;                  // tile * nst + stage
+  const int row = (int)(idx % TN), c = (int)((idx / TN) & 3);
+  const int64_t sidx = idx / (4 * TN);             // tile * nst + stage
   const int st = (int)(sidx % nst);
-  const int64_t j = (sidx / nst) * GN + row, k = (int64_t)st * (4 * KCH) + c * KCH;
+  const int64_t j = (sidx / nst) * TN + row, k = (int64_t)st * (4 * KCH) + c * KCH;
   float v[KCH];
 #pragma unroll
   for (int e = 0; e < KCH; ++e) v[e] = (j < J && k + e < K) ? __ldg(B + j * sb_j + (k + e) * sb_k) : 0.f;
   uint32_t h[4], l[4];
   split_chunk<KCH>(v, h, l);
-  uint8_t* dst = out + sidx * (2 * kBHalf) + (size_t)c * (GN * 16) + (size_t)row * 16;
+  uint8_t* dst = out + sidx * (2 * TN * 64) + (size_t)c * (TN * 16) + (size_t)row * 16;
   *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
-  *reinterpret_cast<uint4*>(dst + kBHalf) = make_uint4(l[0], l[1], l[2], l[3]);
+  *reinterpret_cast<uint4*>(dst + TN * 64) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 constexpr int kWorkers = 256;              // warps 0..7 stage A and run the epilogue; warp 8 drives the TMA and the UMMAs
 
-// DUAL = false: one accumulator, 2 stages, 2 CTAs per SM (one CTA's epilogue overlaps the other's main loop).
-// DUAL = true:  the head product a_hi*b_hi accumulates in TMEM columns [0,256), the two cross products in [256,512), added
-//               in the epilogue in fp32.  The tensor core's fp32 accumulate truncates, a bias that compounds layer by layer
-//               through the MLP's forward / dX chain; the main accumulator now sees a third of the UMMAs and the cross
-//               accumulator is 2^-11 of its magnitude.  All of TMEM -> one CTA per SM, 4 stages.
+// DUAL = false: 128 x 256 tile, one accumulator (256 TMEM columns), 2 stages of 48 KB.
+// DUAL = true:  128 x 128 tile; the head product a_hi*b_hi accumulates in TMEM columns [0,128), the two cross products in
+//               [128,256), added in the epilogue in fp32; 3 stages of 32 KB.  The tensor core's fp32 accumulate truncates,
+//               a bias that compounds layer by layer through the MLP's forward / dX chain; the main accumulator now sees a
+//               third of the UMMAs and the cross accumulator is 2^-11 of its magnitude.
+// Either way 96 KB of shared memory and 256 TMEM columns: two CTAs per SM, one's epilogue under the other's main loop.
 template <int KCH, bool AKC, bool DUAL>
-__global__ void __launch_bounds__(kWorkers + 32, DUAL ? 1 : 2) tc_gemm_packed_kernel(GemmArgs g, const uint8_t* __restrict__ bpack) {
+__global__ void __launch_bounds__(kWorkers + 32, 2) tc_gemm_packed_kernel(GemmArgs g, const uint8_t* __restrict__ bpack) {
   constexpr int GK = 4 * KCH;
-  constexpr int NS = DUAL ? 4 : kStages;      // smem stages (power of two)
-  constexpr int PD = NS - 1;                  // the TMA runs this many stages ahead of the UMMAs
-  constexpr uint32_t kCols = DUAL ? 512 : 256;
+  constexpr int TN = DUAL ? 128 : 256;                      // output columns per CTA
+  constexpr uint32_t kBH = TN * 64;                         // bytes of one part (hi or lo) of the B stage
+  constexpr uint32_t kStg = 2 * kAHalf + 2 * kBH;
+  constexpr int NS = DUAL ? 3 : 2;                          // smem stages
+  constexpr int PD = NS - 1;                                // the TMA runs this many stages ahead of the UMMAs
+  static_assert(NS * kStg <= kSmem, "stages must fit in 96 KB");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t empty_bar[NS], full_bar[NS], aready_bar[NS];
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t i0 = (int64_t)blockIdx.x * GM;
-  const int j0 = (int)blockIdx.y * GN;
-  const int jn = (g.J - j0 < GN) ? g.J - j0 : GN;
+  const int j0 = (int)blockIdx.y * TN;
+  const int jn = (g.J - j0 < TN) ? g.J - j0 : TN;
   const int n_mma = (jn + 15) & ~15;
   const int im = (g.I - i0 < GM) ? (int)(g.I - i0) : GM;
   const int nkt = (int)((g.K + GK - 1) / GK);
@@ -472,7 +476,7 @@ __global__ void __launch_bounds__(kWorkers + 32, DUAL ? 1 : 2) tc_gemm_packed_ke
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 8) { ptx::tmem_alloc(ptx::smem_u32(&s_tmem), kCols); ptx::tmem_relinquish(); }
+  if (warp == 8) { ptx::tmem_alloc(ptx::smem_u32(&s_tmem), 256); ptx::tmem_relinquish(); }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -480,20 +484,20 @@ __global__ void __launch_bounds__(kWorkers + 32, DUAL ? 1 : 2) tc_gemm_packed_ke
 
   if (warp == 8) {
     if (lane == 0) {
-      const uint8_t* src = bpack + (size_t)blockIdx.y * nkt * (2 * kBHalf);
+      const uint8_t* src = bpack + (size_t)blockIdx.y * nkt * (2 * kBH);
       const uint32_t idesc = KCH == 8 ? ptx::idesc_bf16(n_mma) : idesc_tf32(n_mma);
       auto load_b = [&](int t) {   // weights of stage t -> slot t % NS
-        const uint32_t slot = smem0 + (uint32_t)(t & (NS - 1)) * kStage;
-        const uint32_t bar = ptx::smem_u32(&full_bar[t & (NS - 1)]);
-        ptx::mbar_arrive_expect_tx(bar, 2 * kBHalf);
-        ptx::bulk_g2s(slot + 2 * kAHalf, src + (size_t)t * (2 * kBHalf), 2 * kBHalf, bar);
+        const uint32_t slot = smem0 + (uint32_t)(t % NS) * kStg;
+        const uint32_t bar = ptx::smem_u32(&full_bar[t % NS]);
+        ptx::mbar_arrive_expect_tx(bar, 2 * kBH);
+        ptx::bulk_g2s(slot + 2 * kAHalf, src + (size_t)t * (2 * kBH), 2 * kBH, bar);
       };
       for (int t = 0; t < PD && t < nkt; ++t) load_b(t);
-      const uint32_t cross = DUAL ? tmem + 256 : tmem;
+      const uint32_t cross = DUAL ? tmem + TN : tmem;
       for (int kt = 0; kt < nkt; ++kt) {
-        const int s = kt & (NS - 1);
+        const int s = kt % NS;
         const uint32_t par = (uint32_t)(kt / NS) & 1u;
-        const uint32_t slot = smem0 + (uint32_t)s * kStage;
+        const uint32_t slot = smem0 + (uint32_t)s * kStg;
         gemm_wait(ptx::smem_u32(&aready_bar[s]), par, 4);
         gemm_wait(ptx::smem_u32(&full_bar[s]), par, 5);
         ptx::tc_fence_after();
@@ -501,8 +505,8 @@ __global__ void __launch_bounds__(kWorkers + 32, DUAL ? 1 : 2) tc_gemm_packed_ke
         for (int ks = 0; ks < 2; ++ks) {
           const uint64_t a_hi = ptx::smem_desc(slot + ks * (2 * GM * 16), GM * 16, 128);
           const uint64_t a_lo = ptx::smem_desc(slot + kAHalf + ks * (2 * GM * 16), GM * 16, 128);
-          const uint64_t b_hi = ptx::smem_desc(slot + 2 * kAHalf + ks * (2 * GN * 16), GN * 16, 128);
-          const uint64_t b_lo = ptx::smem_desc(slot + 2 * kAHalf + kBHalf + ks * (2 * GN * 16), GN * 16, 128);
+          const uint64_t b_hi = ptx::smem_desc(slot + 2 * kAHalf + ks * (2 * TN * 16), TN * 16, 128);
+          const uint64_t b_lo = ptx::smem_desc(slot + 2 * kAHalf + kBH + ks * (2 * TN * 16), TN * 16, 128);
           const uint32_t acc0 = (kt > 0 || ks > 0) ? 1u : 0u;
           if constexpr (KCH == 8) {
             ptx::mma_bf16_ss(cross, a_lo, b_hi, idesc, acc0);
@@ -516,7 +520,7 @@ __global__ void __launch_bounds__(kWorkers + 32, DUAL ? 1 : 2) tc_gemm_packed_ke
         }
         ptx::mma_commit(ptx::smem_u32(&empty_bar[s]));
         if (kt + PD < nkt) {   // stage kt + PD reuses the slot of stage kt - 1: free once those UMMAs have retired
-          if (kt >= 1) gemm_wait(ptx::smem_u32(&empty_bar[(kt - 1) & (NS - 1)]), (uint32_t)((kt - 1) / NS) & 1u, 3);
+          if (kt >= 1) gemm_wait(ptx::smem_u32(&empty_bar[(kt - 1) % NS]), (uint32_t)((kt - 1) / NS) & 1u, 3);
           load_b(kt + PD);
         }
       }
@@ -529,8 +533,8 @@ __global__ void __launch_bounds__(kWorkers + 32, DUAL ? 1 : 2) tc_gemm_packed_ke
     r0.fetch(g.A, a_s, g.I, i0, 0, g.K, GM, tid);
     if (nkt > 1) r1.fetch(g.A, a_s, g.I, i0, GK, g.K, GM, tid);
     auto step = [&](auto& r, int kt) {
-      const int s = kt & (NS - 1);
-      const uint32_t slot = smem0 + (uint32_t)s * kStage;
+      const int s = kt % NS;
+      const uint32_t slot = smem0 + (uint32_t)s * kStg;
       if (kt >= NS) gemm_wait(ptx::smem_u32(&empty_bar[s]), (uint32_t)(kt / NS - 1) & 1u, 1);
       r.store(slot, slot + kAHalf, GM, tid);
       if (kt + 2 < nkt) r.fetch(g.A, a_s, g.I, i0, (int64_t)(kt + 2) * GK, g.K, GM, tid);
@@ -542,34 +546,41 @@ __global__ void __launch_bounds__(kWorkers + 32, DUAL ? 1 : 2) tc_gemm_packed_ke
       step(r0, kt);
       if (kt + 1 < nkt) step(r1, kt + 1);
     }
-    gemm_wait(ptx::smem_u32(&empty_bar[(nkt - 1) & (NS - 1)]), (uint32_t)((nkt - 1) / NS) & 1u, 2);
+    gemm_wait(ptx::smem_u32(&empty_bar[(nkt - 1) % NS]), (uint32_t)((nkt - 1) / NS) & 1u, 2);
     ptx::tc_fence_after();
-    gemm_epilogue<DUAL>(g, tmem, smem0, warp, lane, i0, j0, im, jn, n_mma, false, true);
+    gemm_epilogue<DUAL ? TN : 0>(g, tmem, smem0, warp, lane, i0, j0, im, jn, n_mma, false, true);
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 8) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, kCols); }
+  if (warp == 8) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 256); }
 }
 
 template <int KCH, bool AKC, bool DUAL>
 int launch_packed_variant(const GemmArgs& a, dim3 grid, cudaStream_t st) {
-  constexpr uint32_t smem = (DUAL ? 4 : kStages) * kStage;
   static bool configured = false;
   if (!configured) {
-    ZEST_CUDA(cudaFuncSetAttribute(tc_gemm_packed_kernel<KCH, AKC, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ZEST_CUDA(cudaFuncSetAttribute(tc_gemm_packed_kernel<KCH, AKC, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
     configured = true;
   }
-  tc_gemm_packed_kernel<KCH, AKC, DUAL><<<grid, kWorkers + 32, smem, st>>>(a, (const uint8_t*)a.b_scratch);
+  tc_gemm_packed_kernel<KCH, AKC, DUAL><<<grid, kWorkers + 32, kSmem, st>>>(a, (const uint8_t*)a.b_scratch);
   ZEST_LAUNCH_CHECK();
   return ZEST_OK;
 }
 
+// bytes of packed weight images a GEMM needs
 template <int KCH, bool DUAL>
-int launch_packed(const GemmArgs& a, dim3 grid, cudaStream_t st) {
-  constexpr int GK = 4 * KCH;
+int64_t packed_bytes(const GemmArgs& a) {
+  constexpr int TN = DUAL ? 128 : 256;
+  return ((a.J + TN - 1) / TN) * ((a.K + 4 * KCH - 1) / (4 * KCH)) * (int64_t)(2 * TN * 64);
+}
+
+template <int KCH, bool DUAL>
+int launch_packed(const GemmArgs& a, cudaStream_t st) {
+  constexpr int GK = 4 * KCH, TN = DUAL ? 128 : 256;
   const int nst = (int)((a.K + GK - 1) / GK);
-  const int64_t total = (int64_t)grid.y * nst * 1024;
-  gemm_pack_b_kernel<KCH><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a.B, a.sb_j, a.sb_k, a.J, a.K, nst, total, (uint8_t*)a.b_scratch);
+  dim3 grid((unsigned)((a.I + GM - 1) / GM), (unsigned)((a.J + TN - 1) / TN), 1);
+  const int64_t total = (int64_t)grid.y * nst * 4 * TN;
+  gemm_pack_b_kernel<KCH, TN><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a.B, a.sb_j, a.sb_k, a.J, a.K, nst, total, (uint8_t*)a.b_scratch);
   ZEST_LAUNCH_CHECK();
   return a.sa_k == 1 ? launch_packed_variant<KCH, true, DUAL>(a, grid, st) : launch_packed_variant<KCH, false, DUAL>(a, grid, st);
 }
@@ -645,9 +656,8 @@ int launch_gemm_tc(const GemmArgs& a0, int engine, cudaStream_t st) {
   ZEST_CHECK_ARG(splits == 1 || (!a.Z && !a.gate && !a.relu && !a.gb_dZ), "tc gemm: split-K cannot fuse a non-linear epilogue");
   dim3 grid((unsigned)ti, (unsigned)tj, (unsigned)splits);
   if (a.b_scratch && splits == 1 && ti >= 8 && !a.rowsum) {   // B is a small matrix re-read by every row tile (weights): pack + TMA
-    const int64_t nst = (a.K + GK - 1) / GK;
-    if (tj * nst * (int64_t)(2 * kBHalf) <= a.b_scratch_bytes)
-      return engine == 1 ? launch_packed<8, false>(a, grid, st) : launch_packed<4, true>(a, grid, st);
+    if (engine == 1 && packed_bytes<8, false>(a) <= a.b_scratch_bytes) return launch_packed<8, false>(a, st);
+    if (engine == 2 && packed_bytes<4, true>(a) <= a.b_scratch_bytes) return launch_packed<4, true>(a, st);
   }
   return bf16 ? launch_prec<8>(a, grid, kper, st) : launch_prec<4>(a, grid, kper, st);
 }
