@@ -238,6 +238,82 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs& g, uint32_t tmem, 
 #pragma unroll
       for (int t = 0; t < 4; ++t) if (t < nv) b4[t] = __ldg(g.bias + j + t);
     }
+    // Fast paths: all four columns valid and every row's pointer 16-byte aligned (aligned first row, row strides multiples of
+    // 4 floats).  Every global load of a batch of rows is issued before the first use (the epilogue is latency-bound otherwise).
+    const auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool in_gb = g.gb_dZ != nullptr && j + 3 >= g.gb_col0;
+    const int jj = j - g.gb_col0;
+    bool fast = nv >= 4 && !atomic;
+    if (in_gb) fast = fast && jj >= 0 && (g.gb_ld & 3) == 0 && al16(g.gb_Z + jj) && al16(g.gb_G + jj) && al16(g.gb_gG + jj) && al16(g.gb_dZ + jj) &&
+                      (!g.accumulate || ((g.ldc & 3) == 0 && al16(g.C + j)));
+    else fast = fast && (g.ldc & 3) == 0 && al16(g.C + j) && (!g.Z || ((g.ldz & 3) == 0 && al16(g.Z + j))) &&
+                (!g.gate || ((g.ldg & 3) == 0 && al16(g.gate + j)));
+    if (fast && !in_gb) {          // forward / plain: [Z = v], v *= gate, relu, [+= C], C = v
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float4 gt4[4], old4[4];
+#pragma unroll
+        for (int r4 = 0; r4 < 4; ++r4) {
+          const int row = q * 32 + (h * 4 + r4) * 4 + rsub;
+          const int64_t i = i0 + row;
+          gt4[r4] = old4[r4] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < im) {
+            if (g.gate) gt4[r4] = __ldg(reinterpret_cast<const float4*>(g.gate + i * g.ldg + j));
+            if (g.accumulate) old4[r4] = *reinterpret_cast<const float4*>(g.C + i * g.ldc + j);
+          }
+        }
+#pragma unroll
+        for (int r4 = 0; r4 < 4; ++r4) {
+          const int lr = (h * 4 + r4) * 4 + rsub, row = q * 32 + lr;
+          const uint4 w = ptx::ld_smem_v4(stg + (uint32_t)lr * kEpiRow + cq * 4);
+          if (row >= im) continue;
+          const int64_t i = i0 + row;
+          float4 v = make_float4(__uint_as_float(w.x) + b4[0], __uint_as_float(w.y) + b4[1], __uint_as_float(w.z) + b4[2], __uint_as_float(w.w) + b4[3]);
+          if (g.Z) *reinterpret_cast<float4*>(g.Z + i * g.ldz + j) = v;
+          if (g.gate) { v.x *= gt4[r4].x; v.y *= gt4[r4].y; v.z *= gt4[r4].z; v.w *= gt4[r4].w; }
+          if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          if (g.accumulate) { v.x += old4[r4].x; v.y += old4[r4].y; v.z += old4[r4].z; v.w += old4[r4].w; }
+          *reinterpret_cast<float4*>(g.C + i * g.ldc + j) = v;
+        }
+      }
+      __syncwarp();
+      continue;
+    }
+    if (fast) {                    // fused gate backward (see GemmArgs): v [+ C] -> dZ, gG
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        float4 zz[2], gg[2], acc[2], old4[2];
+#pragma unroll
+        for (int r2 = 0; r2 < 2; ++r2) {
+          const int row = q * 32 + (h * 2 + r2) * 4 + rsub;
+          const int64_t i = i0 + row, o = i * g.gb_ld + jj;
+          zz[r2] = gg[r2] = acc[r2] = old4[r2] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < im) {
+            zz[r2] = __ldg(reinterpret_cast<const float4*>(g.gb_Z + o));
+            gg[r2] = __ldg(reinterpret_cast<const float4*>(g.gb_G + o));
+            acc[r2] = *reinterpret_cast<const float4*>(g.gb_gG + o);
+            if (g.accumulate) old4[r2] = *reinterpret_cast<const float4*>(g.C + i * g.ldc + j);
+          }
+        }
+#pragma unroll
+        for (int r2 = 0; r2 < 2; ++r2) {
+          const int lr = (h * 2 + r2) * 4 + rsub, row = q * 32 + lr;
+          const uint4 w = ptx::ld_smem_v4(stg + (uint32_t)lr * kEpiRow + cq * 4);
+          if (row >= im) continue;
+          const int64_t o = (i0 + row) * g.gb_ld + jj;
+          const float v0 = __uint_as_float(w.x) + b4[0] + old4[r2].x, v1 = __uint_as_float(w.y) + b4[1] + old4[r2].y;
+          const float v2 = __uint_as_float(w.z) + b4[2] + old4[r2].z, v3 = __uint_as_float(w.w) + b4[3] + old4[r2].w;
+          const float m0 = (zz[r2].x * gg[r2].x > 0.f) ? v0 : 0.f, m1 = (zz[r2].y * gg[r2].y > 0.f) ? v1 : 0.f;
+          const float m2 = (zz[r2].z * gg[r2].z > 0.f) ? v2 : 0.f, m3 = (zz[r2].w * gg[r2].w > 0.f) ? v3 : 0.f;
+          *reinterpret_cast<float4*>(g.gb_dZ + o) = make_float4(m0 * gg[r2].x, m1 * gg[r2].y, m2 * gg[r2].z, m3 * gg[r2].w);
+          *reinterpret_cast<float4*>(g.gb_gG + o) = make_float4(acc[r2].x + m0 * zz[r2].x, acc[r2].y + m1 * zz[r2].y,
+                                                                acc[r2].z + m2 * zz[r2].z, acc[r2].w + m3 * zz[r2].w);
+        }
+      }
+      __syncwarp();
+      continue;
+    }
+    // generic path: ragged edges, misaligned rows (the skip layer's [pe | h] blocks), split-K atomics
 #pragma unroll 2
     for (int rr = 0; rr < 32; rr += 4) {
       const int row = q * 32 + rr + rsub;
@@ -459,8 +535,11 @@ __global__ void __launch_bounds__(kWorkers + 32, 2) tc_gemm_packed_kernel(GemmAr
   __shared__ __align__(8) uint64_t empty_bar[NS], full_bar[NS], aready_bar[NS];
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t i0 = (int64_t)blockIdx.x * GM;
-  const int j0 = (int)blockIdx.y * TN;
+  // column tiles of one row tile are adjacent CTAs: the second reader of an A tile hits L2
+  const int tiles_n = (g.J + TN - 1) / TN;
+  const int bn = (int)(blockIdx.x % tiles_n);
+  const int64_t i0 = (int64_t)(blockIdx.x / tiles_n) * GM;
+  const int j0 = bn * TN;
   const int jn = (g.J - j0 < TN) ? g.J - j0 : TN;
   const int n_mma = (jn + 15) & ~15;
   const int im = (g.I - i0 < GM) ? (int)(g.I - i0) : GM;
@@ -484,7 +563,7 @@ __global__ void __launch_bounds__(kWorkers + 32, 2) tc_gemm_packed_kernel(GemmAr
 
   if (warp == 8) {
     if (lane == 0) {
-      const uint8_t* src = bpack + (size_t)blockIdx.y * nkt * (2 * kBH);
+      const uint8_t* src = bpack + (size_t)bn * nkt * (2 * kBH);
       const uint32_t idesc = KCH == 8 ? ptx::idesc_bf16(n_mma) : idesc_tf32(n_mma);
       auto load_b = [&](int t) {   // weights of stage t -> slot t % NS
         const uint32_t slot = smem0 + (uint32_t)(t % NS) * kStg;
@@ -527,24 +606,27 @@ __global__ void __launch_bounds__(kWorkers + 32, 2) tc_gemm_packed_kernel(GemmAr
     }
     __syncwarp();
   } else {
-    // workers: A two stages ahead in registers (two static register sets), no CTA-wide barrier in the loop
-    typename StagePick<KCH, AKC, GM>::type r0, r1;
+    // workers: A NSET stages ahead in registers (static register sets), no CTA-wide barrier in the loop
+    constexpr int NSET = KCH == 4 ? 4 : 2;     // a tf32 stage is 8 registers per thread, a bf16 stage 16
+    typename StagePick<KCH, AKC, GM>::type rs[NSET];
     const int64_t a_s = AKC ? g.sa_i : g.sa_k;
-    r0.fetch(g.A, a_s, g.I, i0, 0, g.K, GM, tid);
-    if (nkt > 1) r1.fetch(g.A, a_s, g.I, i0, GK, g.K, GM, tid);
+#pragma unroll
+    for (int u = 0; u < NSET; ++u)
+      if (u < nkt) rs[u].fetch(g.A, a_s, g.I, i0, (int64_t)u * GK, g.K, GM, tid);
     auto step = [&](auto& r, int kt) {
       const int s = kt % NS;
       const uint32_t slot = smem0 + (uint32_t)s * kStg;
       if (kt >= NS) gemm_wait(ptx::smem_u32(&empty_bar[s]), (uint32_t)(kt / NS - 1) & 1u, 1);
       r.store(slot, slot + kAHalf, GM, tid);
-      if (kt + 2 < nkt) r.fetch(g.A, a_s, g.I, i0, (int64_t)(kt + 2) * GK, g.K, GM, tid);
+      if (kt + NSET < nkt) r.fetch(g.A, a_s, g.I, i0, (int64_t)(kt + NSET) * GK, g.K, GM, tid);
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&aready_bar[s]));
     };
-    for (int kt = 0; kt < nkt; kt += 2) {
-      step(r0, kt);
-      if (kt + 1 < nkt) step(r1, kt + 1);
+    for (int kt = 0; kt < nkt; kt += NSET) {
+#pragma unroll
+      for (int u = 0; u < NSET; ++u)
+        if (kt + u < nkt) step(rs[u], kt + u);
     }
     gemm_wait(ptx::smem_u32(&empty_bar[(nkt - 1) % NS]), (uint32_t)((nkt - 1) / NS) & 1u, 2);
     ptx::tc_fence_after();
@@ -578,8 +660,10 @@ template <int KCH, bool DUAL>
 int launch_packed(const GemmArgs& a, cudaStream_t st) {
   constexpr int GK = 4 * KCH, TN = DUAL ? 128 : 256;
   const int nst = (int)((a.K + GK - 1) / GK);
-  dim3 grid((unsigned)((a.I + GM - 1) / GM), (unsigned)((a.J + TN - 1) / TN), 1);
-  const int64_t total = (int64_t)grid.y * nst * 4 * TN;
+  const int64_t tiles_m = (a.I + GM - 1) / GM, tiles_n = (a.J + TN - 1) / TN;
+  ZEST_CHECK_ARG(tiles_m * tiles_n < (1ll << 31), "tc gemm: shape too large for one launch");
+  dim3 grid((unsigned)(tiles_m * tiles_n), 1, 1);
+  const int64_t total = tiles_n * nst * 4 * TN;
   gemm_pack_b_kernel<KCH, TN><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a.B, a.sb_j, a.sb_k, a.J, a.K, nst, total, (uint8_t*)a.b_scratch);
   ZEST_LAUNCH_CHECK();
   return a.sa_k == 1 ? launch_packed_variant<KCH, true, DUAL>(a, grid, st) : launch_packed_variant<KCH, false, DUAL>(a, grid, st);
