@@ -284,6 +284,37 @@ def fine_tune_stage(sc, dev, lib, H, W, steps=4, warmup=2, engines=(2, 1), rays=
     return out
 
 
+def sf_loss_stage(dev, pk, H, W, rays=4096, reps=10):
+    """"Next" row f4: the scene-flow reductions of one training step (train.py:480-510: two smoothness + two
+    least-kinetic-energy terms) forward + backward on the CUDA path, against the HBM copy bandwidth."""
+    import torch
+    from zest_nerf_b200 import losses as zl
+    g = torch.Generator(device=dev).manual_seed(1)
+    ref = (torch.rand((1, rays, S, 3), device=dev, generator=g) * 2 - 1).requires_grad_(True)
+    post = (ref.detach() + 0.05 * torch.randn((1, rays, S, 3), device=dev, generator=g)).requires_grad_(True)
+    prev = (ref.detach() + 0.05 * torch.randn((1, rays, S, 3), device=dev, generator=g)).requires_grad_(True)
+    pp = (ref.detach() + 0.1 * torch.randn((1, rays, S, 3), device=dev, generator=g)).requires_grad_(True)
+    f = 0.9 * W
+
+    def once():
+        for t in (ref, post, prev, pp):
+            t.grad = None
+        loss = (zl.compute_sf_smooth_loss(ref, post, H, W, f) + zl.compute_sf_smooth_loss(ref, prev, H, W, f)
+                + zl.compute_sf_lke_loss(ref, post, prev, H, W, f) + zl.compute_sf_lke_loss(post, pp, ref, H, W, f))
+        loss.backward()
+    once()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(reps):
+        once()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    byts = rays * S * (2 * 24 + 2 * 36) * 3        # forward reads; backward reads them again and writes as many gradient bytes
+    return {"kernels": "sf_smooth_{fwd,bwd}_kernel x2, sf_lke_{fwd,bwd}_kernel x2 (zest_sf_*_loss_*)", "rays": rays, "ms_per_step": ms,
+            "achieved_gbs": byts / ms / 1e6, "peak_gbs": pk["hbm_gbs"], "frac": byts / ms / 1e6 / pk["hbm_gbs"], "bytes_per_step": byts,
+            "note": "8 launches over 0.2 GB: launch / autograd-bound at this batch size, not bandwidth-bound"}
+
+
 FT_ENGINE_NAMES = {0: "fp32 CUDA cores (sgemm)", 1: "tcgen05 3 x bf16, one accumulator", 2: "tcgen05 3 x tf32, split accumulators (default)"}
 
 
@@ -646,6 +677,10 @@ def main():
     if rank == 0 and world == 1 and c["dynamic"] and not args.no_fine_tune:
         ft = fine_tune_report(fine_tune_stage(sc, dev, lib, H, W, steps=3, warmup=2, engines=(2, 1)), V, pk)
 
+    f4 = None
+    if rank == 0 and world == 1 and not args.no_fine_tune:
+        f4 = sf_loss_stage(dev, pk, H, W)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, sample = cpu_reference(args.config, 4096, 2)
@@ -660,7 +695,7 @@ def main():
                            "l2": "256 MiB buffer written between timed steps (L2 flush); per-step working set 3.6 GB > L2",
                            "parallelism": f"ray-sharded x{world}, one NCCL frame broadcast per step" if world > 1 else "1 GPU"},
                 "steps_ms": [round(x, 3) for x in ms], "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
-                "gather_stage": gstage, "fine_tune": ft, "next_rows": {"f1_ray_builder": f1}}
+                "gather_stage": gstage, "fine_tune": ft, "next_rows": {"f1_ray_builder": f1, "f4_sf_losses": f4}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

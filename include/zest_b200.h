@@ -21,6 +21,9 @@
  *                                         launch (gather + PE + tensor-core MLP): the inference hot path
  *   zest_build_rays                       utils.py:133-230 get_rays_mvs + :290-394 build_rays_base +
  *                                         :232-288 get_ndc_coordinate ("next" row f1)
+ *   zest_sf_smooth_loss_fwd / _bwd        losses.py:142-161 compute_sf_smooth_loss            ("next" row f4)
+ *   zest_sf_lke_loss_fwd / _bwd           losses.py:164-203 compute_sf_lke_loss
+ *   zest_project_ndc_fwd / _bwd           utils.py:516-539 projection_from_ndc (+ :507-514 NDC2Euclidean)
  *
  * Conventions
  *   - Every pointer is a DEVICE pointer into memory owned by the caller (PyTorch); the library
@@ -154,6 +157,32 @@ int zest_mlp_fwd_tc_x(const zest_net* net, const float* x, int ldx, int64_t M, f
 int zest_build_rays(const float* ys, const float* xs, int64_t r0, int W_tgt, const float* cam,
                     int W_src, int H_src, int pad, const float* t_vals, const float* t_rand, int64_t R,
                     int S, float* rays_pts, float* rays_dir, float* rays_ndc, float* depth, void* stream);
+
+/* ---- scene-flow reductions of the training step ("next" row f4) -----------------------------------
+ * All three go through utils.NDC2Euclidean (utils.py:507-514) with the image size H, W and focal length f.
+ * pts_* are the [R, S, 3] NDC sample positions the render path returns (raw_pts_ref / _post / _prev / _pp).
+ * The forward entry points ADD the un-normalised sum to *loss_sum (double, device; the caller zeroes it and divides by
+ * the element count); the backward ones take the upstream gradient of the MEAN loss as a device scalar g_loss and write
+ * (not accumulate) the point gradients; any of them may be NULL.
+ * zest_sf_smooth_loss: losses.py:142-161 compute_sf_smooth_loss - mean |sf_s - sf_{s+1}| over samples s < n_close - 1 of
+ *   sf = E(pts_1) - E(pts_2), n_close = int(0.95 S); element count R (n_close - 1) 3.
+ * zest_sf_lke_loss: losses.py:164-203 compute_sf_lke_loss - 0.5 mean ((E(post) - E(ref)) - (E(ref) - E(prev)))^2 over
+ *   s < n_close = int(0.9 S); loss_sum receives the sum of squares; element count R n_close 3. */
+int zest_sf_smooth_loss_fwd(const float* pts_1, const float* pts_2, int64_t R, int S, int n_close, int H, int W,
+                            float f, double* loss_sum, void* stream);
+int zest_sf_smooth_loss_bwd(const float* pts_1, const float* pts_2, int64_t R, int S, int n_close, int H, int W,
+                            float f, const float* g_loss, float* g_pts_1, float* g_pts_2, void* stream);
+int zest_sf_lke_loss_fwd(const float* pts_ref, const float* pts_post, const float* pts_prev, int64_t R, int S,
+                         int n_close, int H, int W, float f, double* loss_sum, void* stream);
+int zest_sf_lke_loss_bwd(const float* pts_ref, const float* pts_post, const float* pts_prev, int64_t R, int S,
+                         int n_close, int H, int W, float f, const float* g_loss, float* g_ref, float* g_post,
+                         float* g_prev, void* stream);
+/* utils.py:516-539 projection_from_ndc: pts_2d[r] = pixel of w2c * E(sum_s weights[r,s] raw_pts[r,s,:]).  w2c: device
+ * pointer to a row-major 4x4 world-to-camera matrix.  Backward: g_pts_2d [R,2] -> g_weights [R,S], g_raw_pts [R,S,3]. */
+int zest_project_ndc_fwd(const float* w2c, const float* weights, const float* raw_pts, int64_t R, int S, int H, int W,
+                         float f, float* pts_2d, void* stream);
+int zest_project_ndc_bwd(const float* w2c, const float* weights, const float* raw_pts, int64_t R, int S, int H, int W,
+                         float f, const float* g_pts_2d, float* g_weights, float* g_raw_pts, void* stream);
 
 /* ---- alpha compositing (warp per ray) ---------------------------------------------------- */
 /* raw [R*S, ld_raw] (rgb_raw 3, sigma_raw 1, ...), z [R,S], cos_angle [R], noise [R,S] or NULL

@@ -312,3 +312,36 @@ def rendering(args, rays_pts, rays_ndc, depth_candidates, rays_dir,
     else:
         ret["raw_pts_pp"] = ndc_pp
     return ret
+
+
+# --------------------------------------------------------------------------- "next" row f4: scene-flow reductions
+def ndc_to_euclidean(p, H, W, f):
+    """`utils.py:507-514` NDC2Euclidean: depth from the clamped NDC z, then x / y scaled by it (same op order)."""
+    z = p[..., 2:3].clamp(-1.0, 0.99)
+    ze = 2.0 / (z - 1.0)
+    xe = (-p[..., 0:1]) * ze * W / (2.0 * f)
+    ye = (-p[..., 1:2]) * ze * H / (2.0 * f)
+    return torch.cat([xe, ye, ze], dim=-1)
+
+
+def sf_smooth_loss(p1, p2, H, W, f):
+    """`losses.py:142-161` compute_sf_smooth_loss: L1 difference of neighbouring scene flows, closest 95 % of the samples."""
+    n = int(p1.shape[-2] * 0.95)
+    flow = ndc_to_euclidean(p1[..., :n, :], H, W, f) - ndc_to_euclidean(p2[..., :n, :], H, W, f)
+    return (flow[..., :-1, :] - flow[..., 1:, :]).abs().mean()
+
+
+def sf_lke_loss(ref, post, prev, H, W, f):
+    """`losses.py:164-203` compute_sf_lke_loss: 0.5 mean (forward flow - backward flow)^2, closest 90 % of the samples."""
+    n = int(ref.shape[-2] * 0.9)
+    e_ref, e_post, e_prev = (ndc_to_euclidean(t[..., :n, :], H, W, f) for t in (ref, post, prev))
+    return 0.5 * (((e_post - e_ref) - (e_ref - e_prev)) ** 2).mean()
+
+
+def project_from_ndc(w2c, H, W, f, weights, raw_pts):
+    """`utils.py:516-539` projection_from_ndc (+ se3_transform_points, perspective_projection): expected NDC point per ray
+    -> Euclidean -> camera frame -> pixel."""
+    p = (weights[..., None] * raw_pts).sum(-2)
+    e = ndc_to_euclidean(p, H, W, f)
+    loc = (w2c[..., :3, :3] @ e[..., :3].unsqueeze(-1) + w2c[..., :3, 3:]).squeeze(-1)
+    return torch.cat([loc[..., 0:1] * f / -loc[..., 2:3] + W / 2.0, -loc[..., 1:2] * f / -loc[..., 2:3] + H / 2.0], dim=-1)

@@ -623,3 +623,50 @@ def test_gradients_match_reference_autograd(zops, name):
     CUDA-core GEMM engine (max-abs bar) and the default tensor-core engine (relative-L2 bar; see _grad_check)."""
     sc, rays, mode, _ = build_case(name)
     _grad_check(zops, sc, rays, mode, label=name, engines=((0, 2e-3, None), (2, 2e-3, 1e-2)))
+
+
+# ----------------------------------------------------------------------------- scene-flow reductions (next row f4)
+def test_scene_flow_losses_match_reference_golden(zops):
+    """compute_sf_smooth_loss / compute_sf_lke_loss / projection_from_ndc on the CUDA path (csrc/losses.cu) against the
+    reference's own outputs and autograd gradients (tests/golden/losses.npz): values <= 1e-5 relative, gradients <= 1e-5 of
+    their max (the L1 term's sign() flips only where two neighbouring flows agree to the last bit)."""
+    import os
+    from zest_nerf_b200 import losses as zl
+    from tests.golden.make_golden_losses import build_loss_case, evaluate
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "losses.npz"))
+    case = {k: v.to(DEV) for k, v in build_loss_case().items()}
+    got = evaluate((zl.compute_sf_smooth_loss, zl.compute_sf_lke_loss, zl.projection_from_ndc), case)
+    for k in gold.files:
+        w = torch.from_numpy(gold[k])
+        err = float((got[k].cpu() - w).abs().max()) / (float(w.abs().max()) + 1e-12)
+        print(f"   {k:10s} rel err {err:.2e}")
+        assert err <= 1e-5, (k, err)
+
+
+def test_scene_flow_losses_edge_cases(zops):
+    """Ragged sample counts (S not a multiple of the warp), every point outside the clamp range (zero z gradient), identical
+    frames (zero loss, zero gradient), against the oracle."""
+    from zest_nerf_b200 import losses as zl
+    from tests.golden.make_golden_losses import H, W, F
+    g = torch.Generator().manual_seed(2)
+    for R, S in ((5, 50), (1, 21), (33, 128)):
+        ref = torch.rand((1, R, S, 3), generator=g) * 2 - 1
+        post = ref + 0.1 * torch.randn((1, R, S, 3), generator=g)
+        prev = ref - 0.1 * torch.randn((1, R, S, 3), generator=g)
+        for name, fn_o, fn_c, args in (("smooth", zo.sf_smooth_loss, zl.compute_sf_smooth_loss, (ref, post)),
+                                       ("lke", zo.sf_lke_loss, zl.compute_sf_lke_loss, (ref, post, prev))):
+            a_o = [t.clone().requires_grad_(True) for t in args]
+            a_c = [t.clone().to(DEV).requires_grad_(True) for t in args]
+            lo, lc = fn_o(*a_o, H, W, F), fn_c(*a_c, H, W, F)
+            lo.backward(); lc.backward()
+            assert abs(float(lc) - float(lo)) <= 1e-5 * abs(float(lo)) + 1e-9, (name, R, S)
+            for to, tc in zip(a_o, a_c):
+                assert float((tc.grad.cpu() - to.grad).abs().max()) <= 1e-5 * float(to.grad.abs().max()) + 1e-9, (name, R, S)
+    far = torch.full((1, 4, 32, 3), 1.5)
+    far_c = far.clone().to(DEV).requires_grad_(True)
+    zl.compute_sf_lke_loss(far_c, far_c * 1.1, far_c * 0.9, H, W, F).backward()
+    assert float(far_c.grad[..., 2].abs().max()) == 0.0            # z > 0.99: clamped, no gradient through depth
+    same = torch.rand((1, 7, 64, 3), generator=g).to(DEV).requires_grad_(True)
+    l = zl.compute_sf_smooth_loss(same, same.detach(), H, W, F) + zl.compute_sf_lke_loss(same, same.detach(), same.detach(), H, W, F)
+    l.backward()
+    assert float(l) == 0.0 and float(same.grad.abs().max()) == 0.0

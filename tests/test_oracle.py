@@ -61,3 +61,19 @@ def test_edge_cases_zero_density_and_tail_sample():
     rgb, depth, acc, w, a = zo.composite_static(raw, z, dists)
     assert torch.allclose(acc, torch.ones_like(acc), atol=1e-6)
     assert float(a[..., -1].min()) == 1.0
+
+
+def test_oracle_scene_flow_losses_match_reference_golden():
+    """"Next" row f4: the oracle's restatement of losses.py:142-203 / utils.py:507-539 against the outputs and autograd
+    gradients of the unmodified reference (tests/golden/losses.npz, written by make_golden_losses.py)."""
+    import os
+    import numpy as np
+    from oracle import zest_oracle as zo
+    from tests.golden.make_golden_losses import build_loss_case, evaluate
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "losses.npz"))
+    got = evaluate((zo.sf_smooth_loss, zo.sf_lke_loss, zo.project_from_ndc), build_loss_case())
+    assert set(gold.files) == set(got)
+    for k in gold.files:
+        w = torch.from_numpy(gold[k])
+        err = float((got[k] - w).abs().max()) / (float(w.abs().max()) + 1e-12)
+        assert err <= 2e-6, (k, err)

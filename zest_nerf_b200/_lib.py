@@ -44,6 +44,12 @@ SIGNATURES = {
     "zest_composite_blend_fwd": (_i, [_p, _i, _p, _i, _p, _p, _p, _l, _i, _f, _p, _p, _p, _p, _p, _p, _p]),
     "zest_composite_blend_bwd": (_i, [_p, _i, _p, _i, _p, _p, _p, _l, _i, _p, _p, _p, _p, _p, _p, _i, _p, _i, _p]),
     "zest_build_rays": (_i, [_p, _p, _l, _i, _p, _i, _i, _i, _p, _p, _l, _i, _p, _p, _p, _p, _p]),
+    "zest_sf_smooth_loss_fwd": (_i, [_p, _p, _l, _i, _i, _i, _i, _f, _p, _p]),
+    "zest_sf_smooth_loss_bwd": (_i, [_p, _p, _l, _i, _i, _i, _i, _f, _p, _p, _p, _p]),
+    "zest_sf_lke_loss_fwd": (_i, [_p, _p, _p, _l, _i, _i, _i, _i, _f, _p, _p]),
+    "zest_sf_lke_loss_bwd": (_i, [_p, _p, _p, _l, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p]),
+    "zest_project_ndc_fwd": (_i, [_p, _p, _p, _l, _i, _i, _i, _f, _p, _p]),
+    "zest_project_ndc_bwd": (_i, [_p, _p, _p, _l, _i, _i, _i, _f, _p, _p, _p, _p]),
     "zest_set_gemm_engine": (_i, [_i]),
     "zest_gemm_f32": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _l, _i, _l, _p, _i, _i, _i, _p, _l, _p]),
     "zest_tc_selftest": (_i, [_p, _p, _p, _i, _i, _i, _p]),
