@@ -345,3 +345,47 @@ def project_from_ndc(w2c, H, W, f, weights, raw_pts):
     e = ndc_to_euclidean(p, H, W, f)
     loc = (w2c[..., :3, :3] @ e[..., :3].unsqueeze(-1) + w2c[..., :3, 3:]).squeeze(-1)
     return torch.cat([loc[..., 0:1] * f / -loc[..., 2:3] + W / 2.0, -loc[..., 1:2] * f / -loc[..., 2:3] + H / 2.0], dim=-1)
+
+
+# --------------------------------------------------------------------------- "next" row f3 (first half): plane-sweep cost volume
+def plane_sweep_grid(proj, depth_values, H, W, pad):
+    """`utils.py:56-94` homo_warp's sampling grid: pixel (x - pad, y - pad, 1) of the padded reference frame on every depth
+    plane -> source view, normalised to [-1, 1].  proj [3, 4] = src_proj @ ref_proj_inv; returns [D, Hp, Wp, 2]."""
+    Hp, Wp = H + 2 * pad, W + 2 * pad
+    ys, xs = torch.meshgrid(torch.arange(Hp, dtype=torch.float32), torch.arange(Wp, dtype=torch.float32), indexing="ij")
+    pix = torch.stack([xs - pad, ys - pad, torch.ones_like(xs)], 0).reshape(3, -1)          # [3, Hp*Wp]
+    D = depth_values.numel()
+    rot = (proj[:, :3] @ pix).unsqueeze(1).expand(3, D, Hp * Wp)
+    src = rot + proj[:, 3].view(3, 1, 1) / depth_values.view(1, D, 1)
+    uv = src[:2] / src[2:]
+    gx = uv[0] / ((W - 1) / 2) - 1
+    gy = uv[1] / ((H - 1) / 2) - 1
+    return torch.stack([gx, gy], -1).view(D, Hp, Wp, 2)
+
+
+def cost_volume(imgs, feats, proj_mats, depth_values, pad=0):
+    """`networks.py:1077-1140` MVSNet.build_volume_cost (eval mode) for B = 1: reference-view image and zero-padded features
+    broadcast over the depth planes, every source view warped by `plane_sweep_grid` + bilinear sampling (zeros padding,
+    align_corners=True), variance over the views with the in-frustum count.  The border of the first 3 channels (uninitialised
+    memory in the reference, `:1101-1103`) is zero here."""
+    _, V, C, H, W = feats.shape
+    D = depth_values.shape[1]
+    Hp, Wp = H + 2 * pad, W + 2 * pad
+    small = F.interpolate(imgs[0], (H, W), mode="bilinear", align_corners=False)             # [V, 3, H, W]
+    out = torch.zeros((1, 3 * V + C, D, Hp, Wp))
+    out[0, :3, :, pad:H + pad, pad:W + pad] = small[0].unsqueeze(1)
+    ref = F.pad(feats[0, 0], (pad, pad, pad, pad)).unsqueeze(1).expand(C, D, Hp, Wp)
+    total, total_sq = ref.clone(), ref ** 2
+    masks = torch.ones((1, V, D, Hp, Wp))
+    for v in range(1, V):
+        grid = plane_sweep_grid(proj_mats[0, v], depth_values[0], H, W, pad)
+        g = grid.view(1, D, Hp * Wp, 2)
+        warped = F.grid_sample(feats[:, v], g, mode="bilinear", padding_mode="zeros", align_corners=True).view(C, D, Hp, Wp)
+        out[0, 3 * v:3 * v + 3] = F.grid_sample(small[v:v + 1], g, mode="bilinear", padding_mode="zeros",
+                                                align_corners=True).view(3, D, Hp, Wp)
+        masks[0, v] = ((grid > -1.0) & (grid < 1.0)).all(-1).float()
+        total = total + warped
+        total_sq = total_sq + warped ** 2
+    count = 1.0 / masks.sum(1)
+    out[0, 3 * V:] = total_sq * count - (total * count) ** 2
+    return out, masks

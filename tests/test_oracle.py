@@ -77,3 +77,17 @@ def test_oracle_scene_flow_losses_match_reference_golden():
         w = torch.from_numpy(gold[k])
         err = float((got[k] - w).abs().max()) / (float(w.abs().max()) + 1e-12)
         assert err <= 2e-6, (k, err)
+
+
+def test_oracle_cost_volume_matches_reference_golden():
+    """"Next" row f3 (first half): the oracle's plane-sweep cost volume against the outputs of the unmodified reference's
+    MVSNet.build_volume_cost (tests/golden/costvol.npz, written by make_golden_costvol.py)."""
+    import os
+    import numpy as np
+    from oracle import zest_oracle as zo
+    from tests.golden.make_golden_costvol import build_costvol_case
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "costvol.npz"))
+    case = build_costvol_case()
+    vol, masks = zo.cost_volume(case["imgs"], case["feats"], case["proj_mats"], case["depth_values"], pad=case["pad"])
+    assert float((vol - torch.from_numpy(gold["img_feat"])).abs().max()) <= 2e-5
+    assert torch.equal(masks, torch.from_numpy(gold["in_masks"]).float())

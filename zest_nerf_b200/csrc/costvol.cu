@@ -1,0 +1,161 @@
+// "Next" row f3, first half: the plane-sweep cost volume that feeds the encoding-volume CNN -
+// networks.py:1077-1140 MVSNet.build_volume_cost + utils.py:49-99 homo_warp, in one pass.
+//
+// The reference materialises, per source view, the [B, 3, D*Hp*Wp] homography grid, a [C, D, Hp, Wp] warped feature volume
+// (grid_sample), its square, two running sums, the masks and finally the variance: ~30 PyTorch kernels and ~10 volume-sized
+// round trips.  Here one thread owns one voxel (d, y, x) of the padded reference frustum: it projects the voxel into every
+// source view (R (x - pad, y - pad, 1) + T / depth, utils.py:77-89), gathers the 4 bilinear corners of the feature map (laid
+// out as planes of channel quads; the maps are a few MB and stay in L1 / L2), keeps sum and sum of
+// squares in registers and writes the image channels, the variance and the in-frustum masks exactly once.
+// HBM-bound on its output: (3 V + C + V) x 4 bytes per voxel.  Forward only (inference: test.py / render_spiral.py).
+#include "common.cuh"
+
+namespace zest {
+namespace {
+
+constexpr int kMaxSrc = 7;   // source views besides the reference
+
+struct Sweep {
+  float r[kMaxSrc][9], t[kMaxSrc][3];
+};
+
+struct Tap {              // bilinear footprint of one voxel in one source view (zeros padding, align_corners=True)
+  int off[4];             // pixel offsets (y * W + x) of nw, ne, sw, se; -1 = outside
+  float w[4];
+  float mask;             // -1 < grid < 1 on both axes (networks.py:1123-1126)
+};
+
+// ATen grid_sampler_2d (bilinear, zeros, align_corners=True) at normalised (gx, gy): GridSampler.cuh:23-31,220-227
+__device__ __forceinline__ void make_tap(float gx, float gy, int H, int W, Tap& t) {
+  t.mask = (gx > -1.f && gx < 1.f && gy > -1.f && gy < 1.f) ? 1.f : 0.f;
+  const float ix = safe_int_range(unnormalize(gx, W)), iy = safe_int_range(unnormalize(gy, H));
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+  const float wx1 = ix - fx, wy1 = iy - fy;
+  const float wx0 = (fx + 1.f) - ix, wy0 = (fy + 1.f) - iy;
+  t.w[0] = wx0 * wy0; t.w[1] = wx1 * wy0; t.w[2] = wx0 * wy1; t.w[3] = wx1 * wy1;
+  const bool xin0 = x0 >= 0 && x0 < W, xin1 = x1 >= 0 && x1 < W, yin0 = y0 >= 0 && y0 < H, yin1 = y1 >= 0 && y1 < H;
+  t.off[0] = (xin0 && yin0) ? y0 * W + x0 : -1;
+  t.off[1] = (xin1 && yin0) ? y0 * W + x1 : -1;
+  t.off[2] = (xin0 && yin1) ? y1 * W + x0 : -1;
+  t.off[3] = (xin1 && yin1) ? y1 * W + x1 : -1;
+}
+
+__device__ __forceinline__ float4 tap4(const float* __restrict__ base, int stride, const Tap& t) {   // 4 consecutive channels
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (t.off[k] < 0) continue;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(base + (int64_t)t.off[k] * stride));
+    o.x += v.x * t.w[k]; o.y += v.y * t.w[k]; o.z += v.z * t.w[k]; o.w += v.w * t.w[k];
+  }
+  return o;
+}
+
+// feats_cl [V, C / 4, H, W, 4]: channel quads as planes of float4 pixels - the 32 lanes of a warp (x-adjacent voxels) then read
+// 32 neighbouring float4 of one plane (4 lines) instead of one float4 out of 32 different 128-byte pixels.
+// imgs_cl [V, H, W, 4] (r, g, b, 0) at feature resolution, depth [D]
+// img_feat [3 V + C, D, Hp, Wp], in_masks [V, D, Hp, Wp]
+template <int NSRC>
+__global__ void __launch_bounds__(256) cost_volume_kernel(const float* __restrict__ feats_cl, const float* __restrict__ imgs_cl, Sweep sw,
+                                                          const float* __restrict__ depth, int C, int H, int W, int D, int pad,
+                                                          float* __restrict__ img_feat, float* __restrict__ in_masks) {
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const int64_t plane = (int64_t)Hp * Wp, vol = plane * D;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= vol) return;
+  const int d = (int)(idx / plane);
+  const int rem = (int)(idx - (int64_t)d * plane);
+  const int y = rem / Wp, x = rem - y * Wp;
+  // utils.py:66-75: pixel grid of the padded reference frame, shifted by -pad
+  const float gx0 = (float)x - (float)pad, gy0 = (float)y - (float)pad;
+  const float dep = __ldg(depth + d);
+  const bool inside = x >= pad && x < W + pad && y >= pad && y < H + pad;     // F.pad(ref_feats, pad) is zero outside
+  const int ref_off = inside ? (y - pad) * W + (x - pad) : -1;
+
+  Tap tap[NSRC];
+  float cnt = 1.f;
+#pragma unroll
+  for (int v = 0; v < NSRC; ++v) {
+    // utils.py:77-89: src = R (x, y, 1) + T / depth; uv = src.xy / src.z; grid = uv / ((size - 1) / 2) - 1
+    float s[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      s[j] = __fadd_rn(dot3(gx0, gy0, 1.f, sw.r[v][3 * j], sw.r[v][3 * j + 1], sw.r[v][3 * j + 2]), __fdiv_rn(sw.t[v][j], dep));
+    const float u = __fdiv_rn(s[0], s[2]), w = __fdiv_rn(s[1], s[2]);
+    const float gx = __fsub_rn(__fdiv_rn(u, (float)(W - 1) / 2.f), 1.f), gy = __fsub_rn(__fdiv_rn(w, (float)(H - 1) / 2.f), 1.f);
+    make_tap(gx, gy, H, W, tap[v]);
+    in_masks[(int64_t)(v + 1) * vol + idx] = tap[v].mask;
+    cnt += tap[v].mask;
+  }
+  in_masks[idx] = 1.f;
+  const float inv = __fdiv_rn(1.0f, cnt);     // networks.py:1137
+
+  // image channels: reference view (zero outside the unpadded window; the reference leaves that border uninitialised,
+  // networks.py:1101-1103), then every warped source view
+  {
+    float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (inside) c0 = __ldg(reinterpret_cast<const float4*>(imgs_cl + (int64_t)ref_off * 4));
+    img_feat[0 * vol + idx] = c0.x; img_feat[1 * vol + idx] = c0.y; img_feat[2 * vol + idx] = c0.z;
+#pragma unroll
+    for (int v = 0; v < NSRC; ++v) {
+      const float4 cv = tap4(imgs_cl + (int64_t)(v + 1) * H * W * 4, 4, tap[v]);
+      img_feat[(int64_t)(3 * (v + 1) + 0) * vol + idx] = cv.x;
+      img_feat[(int64_t)(3 * (v + 1) + 1) * vol + idx] = cv.y;
+      img_feat[(int64_t)(3 * (v + 1) + 2) * vol + idx] = cv.z;
+    }
+  }
+  // variance of the feature channels over the views (networks.py:1105-1138)
+  float* var = img_feat + (int64_t)3 * (NSRC + 1) * vol + idx;
+  for (int c = 0; c < C; c += 4) {
+    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* plane0 = feats_cl + (int64_t)(c >> 2) * H * W * 4;          // view 0, channel quad c / 4
+    const int64_t vstride = (int64_t)(C >> 2) * H * W * 4;
+    if (inside) f = __ldg(reinterpret_cast<const float4*>(plane0 + (int64_t)ref_off * 4));
+    float4 sum = f, sq = make_float4(f.x * f.x, f.y * f.y, f.z * f.z, f.w * f.w);
+#pragma unroll
+    for (int v = 0; v < NSRC; ++v) {
+      const float4 g = tap4(plane0 + (v + 1) * vstride, 4, tap[v]);
+      sum.x += g.x; sum.y += g.y; sum.z += g.z; sum.w += g.w;
+      sq.x += g.x * g.x; sq.y += g.y * g.y; sq.z += g.z * g.z; sq.w += g.w * g.w;
+    }
+    const float mx = sum.x * inv, my = sum.y * inv, mz = sum.z * inv, mw = sum.w * inv;
+    var[(int64_t)(c + 0) * vol] = __fsub_rn(__fmul_rn(sq.x, inv), __fmul_rn(mx, mx));
+    var[(int64_t)(c + 1) * vol] = __fsub_rn(__fmul_rn(sq.y, inv), __fmul_rn(my, my));
+    var[(int64_t)(c + 2) * vol] = __fsub_rn(__fmul_rn(sq.z, inv), __fmul_rn(mz, mz));
+    var[(int64_t)(c + 3) * vol] = __fsub_rn(__fmul_rn(sq.w, inv), __fmul_rn(mw, mw));
+  }
+}
+
+}  // namespace
+}  // namespace zest
+
+using namespace zest;
+
+extern "C" int zest_cost_volume_fwd(const float* feats_cl, const float* imgs_cl, const float* proj_host, const float* depth, int V, int C,
+                                    int H, int W, int D, int pad, float* img_feat, float* in_masks, void* stream) {
+  ZEST_CHECK_ARG(feats_cl && imgs_cl && proj_host && depth && img_feat && in_masks, "zest_cost_volume_fwd: null argument");
+  ZEST_CHECK_ARG(V >= 2 && V - 1 <= kMaxSrc && C > 0 && (C % 4) == 0 && H > 1 && W > 1 && D > 0 && pad >= 0,
+                 "zest_cost_volume_fwd: unsupported shape (V=%d C=%d H=%d W=%d D=%d pad=%d)", V, C, H, W, D, pad);
+  Sweep sw;
+  for (int v = 0; v < V - 1; ++v) {
+    for (int j = 0; j < 3; ++j) {
+      for (int k = 0; k < 3; ++k) sw.r[v][3 * j + k] = proj_host[12 * v + 4 * j + k];
+      sw.t[v][j] = proj_host[12 * v + 4 * j + 3];
+    }
+  }
+  const int64_t vol = (int64_t)D * (H + 2 * pad) * (W + 2 * pad);
+  const unsigned grid = (unsigned)((vol + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (V - 1) {
+    case 1: cost_volume_kernel<1><<<grid, 256, 0, st>>>(feats_cl, imgs_cl, sw, depth, C, H, W, D, pad, img_feat, in_masks); break;
+    case 2: cost_volume_kernel<2><<<grid, 256, 0, st>>>(feats_cl, imgs_cl, sw, depth, C, H, W, D, pad, img_feat, in_masks); break;
+    case 3: cost_volume_kernel<3><<<grid, 256, 0, st>>>(feats_cl, imgs_cl, sw, depth, C, H, W, D, pad, img_feat, in_masks); break;
+    case 4: cost_volume_kernel<4><<<grid, 256, 0, st>>>(feats_cl, imgs_cl, sw, depth, C, H, W, D, pad, img_feat, in_masks); break;
+    default:
+      set_error("zest_cost_volume_fwd: %d source views not instantiated (1..4)", V - 1);
+      return ZEST_E_ARG;
+  }
+  ZEST_LAUNCH_CHECK();
+  return ZEST_OK;
+}
