@@ -123,6 +123,33 @@ def test_tc_gemm_matches_fp32(zops, lib, I, J, K, a_kc, b_kc):
     assert e_bf16 <= 3e-5, f"3 x bf16 GEMM error {e_bf16:.2e} (SIMT fp32: {e_simt:.2e})"
 
 
+@pytest.mark.parametrize("engine", [1, 2])
+def test_tc_gemm_writes_only_its_output(zops, lib, engine):
+    """Guard bands instead of compute-sanitizer (closed on this pool): C lives inside a larger sentinel-filled buffer with a
+    padded row stride; ragged row / column tiles, the packed-weights path, split-K atomics and misaligned rows must leave
+    every sentinel untouched."""
+    g = torch.Generator().manual_seed(17)
+    scratch = torch.empty((2 << 20,), dtype=torch.uint8, device=DEV)
+    for I, J, K, a_kc, b_kc, splits, pad_c in ((1100, 347, 283, True, True, 1, 5), (1100, 256, 347, True, False, 1, 4),
+                                                (300, 63, 100, True, True, 1, 1), (256, 283, 3000, False, False, 16, 3),
+                                                (9, 256, 2500, False, False, 16, 8), (129, 17, 33, True, True, 1, 2)):
+        A = torch.randn((I, K), generator=g)
+        B = torch.randn((J, K), generator=g)
+        Ad = (A if a_kc else A.t().contiguous()).to(DEV)
+        Bd = (B if b_kc else B.t().contiguous()).to(DEV)
+        buf = torch.full((I + 2, J + pad_c), 777.0, device=DEV)
+        Cv = buf[1:I + 1, :J]
+        if splits > 1:
+            Cv.zero_()
+        _gemm(lib, Ad, (K, 1) if a_kc else (1, I), Bd, (K, 1) if b_kc else (1, J), Cv, I, J, K, accumulate=int(splits > 1),
+              splits=splits, engine=engine, scratch=scratch)
+        want = A.double() @ B.double().t()
+        assert float((Cv.cpu().double() - want).abs().max()) <= 3e-5 * float(want.abs().max()), (I, J, K)
+        guard = buf.clone()
+        guard[1:I + 1, :J] = 777.0
+        assert bool((guard == 777.0).all()), f"GEMM {I}x{J}x{K} engine {engine} wrote outside its output"
+
+
 def test_tc_gemm_split_k_accumulates(zops, lib):
     """dW mode: K split over CTAs, atomic accumulation on top of the existing contents of C."""
     g = torch.Generator().manual_seed(99)
