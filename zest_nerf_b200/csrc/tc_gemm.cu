@@ -250,21 +250,18 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs& g, uint32_t tmem, 
                 (!g.gate || ((g.ldg & 3) == 0 && al16(g.gate + j)));
     if (fast && !in_gb) {          // forward / plain: [Z = v], v *= gate, relu, [+= C], C = v
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float4 gt4[4], old4[4];
+      for (int h = 0; h < 1; ++h) {
+        float4 gt4[8];
 #pragma unroll
-        for (int r4 = 0; r4 < 4; ++r4) {
-          const int row = q * 32 + (h * 4 + r4) * 4 + rsub;
+        for (int r4 = 0; r4 < 8; ++r4) {
+          const int row = q * 32 + (h * 8 + r4) * 4 + rsub;
           const int64_t i = i0 + row;
-          gt4[r4] = old4[r4] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row < im) {
-            if (g.gate) gt4[r4] = __ldg(reinterpret_cast<const float4*>(g.gate + i * g.ldg + j));
-            if (g.accumulate) old4[r4] = *reinterpret_cast<const float4*>(g.C + i * g.ldc + j);
-          }
+          gt4[r4] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < im && g.gate) gt4[r4] = __ldg(reinterpret_cast<const float4*>(g.gate + i * g.ldg + j));
         }
 #pragma unroll
-        for (int r4 = 0; r4 < 4; ++r4) {
-          const int lr = (h * 4 + r4) * 4 + rsub, row = q * 32 + lr;
+        for (int r4 = 0; r4 < 8; ++r4) {
+          const int lr = (h * 8 + r4) * 4 + rsub, row = q * 32 + lr;
           const uint4 w = ptx::ld_smem_v4(stg + (uint32_t)lr * kEpiRow + cq * 4);
           if (row >= im) continue;
           const int64_t i = i0 + row;
@@ -272,7 +269,10 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs& g, uint32_t tmem, 
           if (g.Z) *reinterpret_cast<float4*>(g.Z + i * g.ldz + j) = v;
           if (g.gate) { v.x *= gt4[r4].x; v.y *= gt4[r4].y; v.z *= gt4[r4].z; v.w *= gt4[r4].w; }
           if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-          if (g.accumulate) { v.x += old4[r4].x; v.y += old4[r4].y; v.z += old4[r4].z; v.w += old4[r4].w; }
+          if (g.accumulate) {   // rare on this path (two dX GEMMs per pass): read at use
+            const float4 o4 = *reinterpret_cast<const float4*>(g.C + i * g.ldc + j);
+            v.x += o4.x; v.y += o4.y; v.z += o4.z; v.w += o4.w;
+          }
           *reinterpret_cast<float4*>(g.C + i * g.ldc + j) = v;
         }
       }
@@ -281,28 +281,29 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs& g, uint32_t tmem, 
     }
     if (fast) {                    // fused gate backward (see GemmArgs): v [+ C] -> dZ, gG
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        float4 zz[2], gg[2], acc[2], old4[2];
+      for (int h = 0; h < 2; ++h) {
+        float4 zz[4], gg[4], acc[4];
 #pragma unroll
-        for (int r2 = 0; r2 < 2; ++r2) {
-          const int row = q * 32 + (h * 2 + r2) * 4 + rsub;
+        for (int r2 = 0; r2 < 4; ++r2) {
+          const int row = q * 32 + (h * 4 + r2) * 4 + rsub;
           const int64_t i = i0 + row, o = i * g.gb_ld + jj;
-          zz[r2] = gg[r2] = acc[r2] = old4[r2] = make_float4(0.f, 0.f, 0.f, 0.f);
+          zz[r2] = gg[r2] = acc[r2] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (row < im) {
             zz[r2] = __ldg(reinterpret_cast<const float4*>(g.gb_Z + o));
             gg[r2] = __ldg(reinterpret_cast<const float4*>(g.gb_G + o));
             acc[r2] = *reinterpret_cast<const float4*>(g.gb_gG + o);
-            if (g.accumulate) old4[r2] = *reinterpret_cast<const float4*>(g.C + i * g.ldc + j);
           }
         }
 #pragma unroll
-        for (int r2 = 0; r2 < 2; ++r2) {
-          const int lr = (h * 2 + r2) * 4 + rsub, row = q * 32 + lr;
+        for (int r2 = 0; r2 < 4; ++r2) {
+          const int lr = (h * 4 + r2) * 4 + rsub, row = q * 32 + lr;
           const uint4 w = ptx::ld_smem_v4(stg + (uint32_t)lr * kEpiRow + cq * 4);
           if (row >= im) continue;
           const int64_t o = (i0 + row) * g.gb_ld + jj;
-          const float v0 = __uint_as_float(w.x) + b4[0] + old4[r2].x, v1 = __uint_as_float(w.y) + b4[1] + old4[r2].y;
-          const float v2 = __uint_as_float(w.z) + b4[2] + old4[r2].z, v3 = __uint_as_float(w.w) + b4[3] + old4[r2].w;
+          float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (g.accumulate) o4 = *reinterpret_cast<const float4*>(g.C + (i0 + row) * g.ldc + j);   // last layer only: read at use
+          const float v0 = __uint_as_float(w.x) + b4[0] + o4.x, v1 = __uint_as_float(w.y) + b4[1] + o4.y;
+          const float v2 = __uint_as_float(w.z) + b4[2] + o4.z, v3 = __uint_as_float(w.w) + b4[3] + o4.w;
           const float m0 = (zz[r2].x * gg[r2].x > 0.f) ? v0 : 0.f, m1 = (zz[r2].y * gg[r2].y > 0.f) ? v1 : 0.f;
           const float m2 = (zz[r2].z * gg[r2].z > 0.f) ? v2 : 0.f, m3 = (zz[r2].w * gg[r2].w > 0.f) ? v3 : 0.f;
           *reinterpret_cast<float4*>(g.gb_dZ + o) = make_float4(m0 * gg[r2].x, m1 * gg[r2].y, m2 * gg[r2].z, m3 * gg[r2].w);
@@ -562,52 +563,69 @@ __global__ void __launch_bounds__(kWorkers + 32, 2) tc_gemm_packed_kernel(GemmAr
   const uint32_t tmem = s_tmem;
 
   if (warp == 8) {
-    if (lane == 0) {
-      const uint8_t* src = bpack + (size_t)bn * nkt * (2 * kBH);
-      const uint32_t idesc = KCH == 8 ? ptx::idesc_bf16(n_mma) : idesc_tf32(n_mma);
-      auto load_b = [&](int t) {   // weights of stage t -> slot t % NS
-        const uint32_t slot = smem0 + (uint32_t)(t % NS) * kStg;
-        const uint32_t bar = ptx::smem_u32(&full_bar[t % NS]);
-        ptx::mbar_arrive_expect_tx(bar, 2 * kBH);
-        ptx::bulk_g2s(slot + 2 * kAHalf, src + (size_t)t * (2 * kBH), 2 * kBH, bar);
-      };
-      for (int t = 0; t < PD && t < nkt; ++t) load_b(t);
-      const uint32_t cross = DUAL ? tmem + TN : tmem;
-      for (int kt = 0; kt < nkt; ++kt) {
-        const int s = kt % NS;
-        const uint32_t par = (uint32_t)(kt / NS) & 1u;
-        const uint32_t slot = smem0 + (uint32_t)s * kStg;
-        gemm_wait(ptx::smem_u32(&aready_bar[s]), par, 4);
-        gemm_wait(ptx::smem_u32(&full_bar[s]), par, 5);
-        ptx::tc_fence_after();
+    // The issue warp stays converged: every lane polls the barriers, one elected lane issues.  Slot numbers are compile-time
+    // (the stage loop is unrolled by NS), so every descriptor is a warp-uniform base plus an immediate - no per-UMMA
+    // register-to-uniform waterfall (measured ~90 cycles per UMMA in the MLP kernel) on the issue path.
+    const uint8_t* src = bpack + (size_t)bn * nkt * (2 * kBH);
+    const uint32_t idesc = KCH == 8 ? ptx::idesc_bf16(n_mma) : idesc_tf32(n_mma);
+    constexpr uint64_t kHi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;                    // SBO = 128 B, descriptor version 1
+    constexpr uint32_t kALbo = ((uint32_t)(GM * 16) >> 4) << 16, kBLbo = ((uint32_t)(TN * 16) >> 4) << 16;
+    const uint32_t lo0 = (smem0 >> 4) & 0x3FFFu;
+    const uint32_t cross = DUAL ? tmem + TN : tmem;
+    auto load_b = [&](int t, int slot_i) {   // weights of stage t -> slot t % NS (= slot_i)
+      const uint32_t slot = smem0 + (uint32_t)slot_i * kStg;
+      const uint32_t bar = ptx::smem_u32(&full_bar[slot_i]);
+      ptx::mbar_arrive_expect_tx(bar, 2 * kBH);
+      ptx::bulk_g2s(slot + 2 * kAHalf, src + (size_t)t * (2 * kBH), 2 * kBH, bar);
+    };
+    if (ptx::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint64_t a_hi = ptx::smem_desc(slot + ks * (2 * GM * 16), GM * 16, 128);
-          const uint64_t a_lo = ptx::smem_desc(slot + kAHalf + ks * (2 * GM * 16), GM * 16, 128);
-          const uint64_t b_hi = ptx::smem_desc(slot + 2 * kAHalf + ks * (2 * TN * 16), TN * 16, 128);
-          const uint64_t b_lo = ptx::smem_desc(slot + 2 * kAHalf + kBH + ks * (2 * TN * 16), TN * 16, 128);
-          const uint32_t acc0 = (kt > 0 || ks > 0) ? 1u : 0u;
-          if constexpr (KCH == 8) {
-            ptx::mma_bf16_ss(cross, a_lo, b_hi, idesc, acc0);
-            ptx::mma_bf16_ss(cross, a_hi, b_lo, idesc, 1u);
-            ptx::mma_bf16_ss(tmem, a_hi, b_hi, idesc, DUAL ? acc0 : 1u);
-          } else {
-            mma_tf32_ss(cross, a_lo, b_hi, idesc, acc0);
-            mma_tf32_ss(cross, a_hi, b_lo, idesc, 1u);
-            mma_tf32_ss(tmem, a_hi, b_hi, idesc, DUAL ? acc0 : 1u);
+      for (int t = 0; t < PD; ++t)
+        if (t < nkt) load_b(t, t);
+    }
+    __syncwarp();
+    uint32_t par = 0;
+    for (int kt0 = 0; kt0 < nkt; kt0 += NS, par ^= 1u) {
+#pragma unroll
+      for (int u = 0; u < NS; ++u) {
+        const int kt = kt0 + u;
+        if (kt >= nkt) break;
+        gemm_wait(ptx::smem_u32(&aready_bar[u]), par, 4);
+        gemm_wait(ptx::smem_u32(&full_bar[u]), par, 5);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t slot_lo = lo0 + (uint32_t)u * (kStg >> 4);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t a_hi = kHi | (uint64_t)((slot_lo + ks * ((2 * GM * 16) >> 4)) | kALbo);
+            const uint64_t a_lo = kHi | (uint64_t)((slot_lo + (kAHalf >> 4) + ks * ((2 * GM * 16) >> 4)) | kALbo);
+            const uint64_t b_hi = kHi | (uint64_t)((slot_lo + ((2 * kAHalf) >> 4) + ks * ((2 * TN * 16) >> 4)) | kBLbo);
+            const uint64_t b_lo = kHi | (uint64_t)((slot_lo + ((2 * kAHalf + kBH) >> 4) + ks * ((2 * TN * 16) >> 4)) | kBLbo);
+            const uint32_t acc0 = (kt > 0 || ks > 0) ? 1u : 0u;
+            if constexpr (KCH == 8) {
+              ptx::mma_bf16_ss(cross, a_lo, b_hi, idesc, acc0);
+              ptx::mma_bf16_ss(cross, a_hi, b_lo, idesc, 1u);
+              ptx::mma_bf16_ss(tmem, a_hi, b_hi, idesc, DUAL ? acc0 : 1u);
+            } else {
+              mma_tf32_ss(cross, a_lo, b_hi, idesc, acc0);
+              mma_tf32_ss(cross, a_hi, b_lo, idesc, 1u);
+              mma_tf32_ss(tmem, a_hi, b_hi, idesc, DUAL ? acc0 : 1u);
+            }
           }
+          ptx::mma_commit(ptx::smem_u32(&empty_bar[u]));
         }
-        ptx::mma_commit(ptx::smem_u32(&empty_bar[s]));
+        __syncwarp();
         if (kt + PD < nkt) {   // stage kt + PD reuses the slot of stage kt - 1: free once those UMMAs have retired
-          if (kt >= 1) gemm_wait(ptx::smem_u32(&empty_bar[(kt - 1) % NS]), (uint32_t)((kt - 1) / NS) & 1u, 3);
-          load_b(kt + PD);
+          const int pu = (u + NS - 1) % NS;
+          if (kt >= 1) gemm_wait(ptx::smem_u32(&empty_bar[pu]), u == 0 ? (par ^ 1u) : par, 3);
+          if (ptx::elect_one()) load_b(kt + PD, pu);
+          __syncwarp();
         }
       }
     }
-    __syncwarp();
   } else {
     // workers: A NSET stages ahead in registers (static register sets), no CTA-wide barrier in the loop
-    constexpr int NSET = KCH == 4 ? 4 : 2;     // a tf32 stage is 8 registers per thread, a bf16 stage 16
+    constexpr int NSET = KCH == 4 ? 6 : 2;     // a tf32 stage is 8 registers per thread, a bf16 stage 16
     typename StagePick<KCH, AKC, GM>::type rs[NSET];
     const int64_t a_s = AKC ? g.sa_i : g.sa_k;
 #pragma unroll
