@@ -142,6 +142,38 @@ def cpu_reference(cfg, n_rays, repeats, threads=None):
     return n_chunks * chunk / best, torch.get_num_threads(), f"{n_chunks} x {chunk}-ray chunks spread over the frame, best of {repeats}"
 
 
+def torch_gpu_reference(sc, dev, H, W, n_chunks=16, repeats=3):
+    """SURVEY 8d's second comparator: the reference's own PyTorch path ON THE SAME GPU - the oracle port with `fast=True`
+    (the very ATen ops the reference calls: grid_sample 3-D / 2-D, linear, cumprod) with every tensor on the device, in
+    1024-ray chunks like the reference's chunk / netchunk defaults (opt.py:63-66).  CUDA-event time over `n_chunks` chunks
+    spread over the frame, rays resident on the device.  Returns (rays/s, sample description)."""
+    import torch
+    from oracle import zest_oracle as zo
+    from zest_nerf_b200 import rays as zrays
+    chunk = 1024
+    total = H * W // chunk
+    n_chunks = min(n_chunks, total)
+    cpu = lambda t: t.detach().cpu()
+    idxs = [int(i * total / n_chunks) for i in range(n_chunks)]
+    rays = []
+    for i in idxs:
+        pts, rdir, ndc, z = zrays.build_rays_val(H, W, cpu(sc.w2cs), cpu(sc.c2ws), cpu(sc.intrinsics), cpu(sc.near_fars), S, pad=24,
+                                                 chunk=chunk, idx=i)
+        rays.append(tuple(t.to(dev) for t in (pts, ndc, z, rdir)))
+    best = None
+    with torch.no_grad():
+        for rep in range(repeats + 1):          # first repeat is the warm-up
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); e0.record()
+            for pts, ndc, z, rdir in rays:
+                zo.rendering(sc.args, pts, ndc, z, rdir, fast=True, **sc.render_kwargs())
+            e1.record(); torch.cuda.synchronize()
+            if rep > 0:
+                ms = e0.elapsed_time(e1)
+                best = ms if best is None else min(best, ms)
+    return n_chunks * chunk / best * 1e3, f"{n_chunks} x {chunk}-ray chunks spread over the frame, rays resident on the device, best of {repeats}"
+
+
 def run_sharded_frames(args):
     """cfg4: `steps` 1080p target poses; every frame is split into per-rank row slabs (driver.FrameRenderer:
     set_frame = per-frame NCCL broadcast + repack, render_pose = CUDA ray builder + fused kernels on the slab,
@@ -381,9 +413,13 @@ def run_fine_tune(args):
     res = fine_tune_stage(sc, dev, lib, c["H"], c["W"], steps=args.steps, warmup=max(args.warmup, 3), engines=(2, 1, 0))
     rep = fine_tune_report(res, c["V"], pk)
     best = res[2]
-    cpu = None
+    cpu = tgpu = None
     if not args.no_cpu_baseline:
         cpu = cpu_fine_tune(256)
+        try:
+            tgpu = torch_gpu_fine_tune(sc, dev, c["H"], c["W"])
+        except Exception as e:      # a comparator must never take the bench line down
+            tgpu = {"value": None, "error": f"{type(e).__name__}: {e}"[:300]}
     line = {"metric": "rays_per_sec_128_samples_fwd_bwd", "value": best["rays_per_s"], "unit": "rays/s", "n_gpus": 1, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": best["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (3 x tf32 UMMAs per product, fp32 accumulate)", "data": "synthetic",
@@ -395,8 +431,49 @@ def run_fine_tune(args):
                          "peak_source": "bf16_tflops_sustained, " + pk_src,
                          "note": "algorithmic fwd+bwd FLOPs against the bf16 tensor peak (SURVEY 8d cfg5); the default engine issues 3 tf32 "
                                  "UMMAs per product, so its own tensor ceiling is 1/6 of this peak"},
-            "fine_tune": rep, "cpu_baseline": cpu}
+            "fine_tune": rep, "cpu_baseline": cpu, "torch_gpu_baseline": tgpu}
     print(json.dumps(line), flush=True)
+
+
+def torch_gpu_fine_tune(sc, dev, H, W, n_rays=1024, repeats=2):
+    """The same step through stock PyTorch ops + autograd ON THE SAME GPU (oracle port, fast=True), a bounded batch."""
+    import torch
+    from oracle import zest_oracle as zo
+    from zest_nerf_b200 import rays as zrays
+    g = torch.Generator().manual_seed(5)
+    lin = torch.randperm(H * W, generator=g)[:n_rays].sort().values
+    t_rand = torch.rand((n_rays, S), generator=g)
+    cpu = lambda t: t.detach().cpu()
+    pts, rdir, ndc, z = zrays.build_rays_val(H, W, cpu(sc.w2cs), cpu(sc.c2ws), cpu(sc.intrinsics), cpu(sc.near_fars), n_samples=S, pad=24,
+                                             pixels=((lin // W).float(), (lin % W).float()), t_rand=t_rand)
+    d = [t.to(dev) for t in (pts, ndc, z, rdir)]
+    vs, vd = sc.vol_static, sc.vol_dynamic
+    sc.vol_static = vs.detach().clone().requires_grad_(True)
+    sc.vol_dynamic = vd.detach().clone().requires_grad_(True)
+    params = [p for net in (sc.net_static, sc.net_dynamic) for p in net.parameters()]
+    mode = dict(val=False, chain_bwd=False, chain_5frames=False, raw_noise_std=0)
+    best = None
+    try:
+        for rep in range(repeats + 1):
+            for p in params:
+                p.grad = None
+            sc.vol_static.grad = sc.vol_dynamic.grad = None
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); e0.record()
+            ret = zo.rendering(sc.args, *d, fast=True, **{**sc.render_kwargs(), **mode})
+            loss = sum((v ** 2).mean() for v in ret.values() if v is not None and v.requires_grad)
+            loss.backward()
+            e1.record(); torch.cuda.synchronize()
+            if rep > 0:
+                ms = e0.elapsed_time(e1)
+                best = ms if best is None else min(best, ms)
+    finally:
+        sc.vol_static, sc.vol_dynamic = vs, vd
+        for p in params:
+            p.grad = None
+        torch.cuda.empty_cache()
+    return {"value": n_rays / best * 1e3, "unit": "rays/s", "kind": "port", "sample": f"{n_rays}-ray batch, best of {repeats}",
+            "how": "the reference's PyTorch ops + autograd (oracle port, fast=True) with all tensors on this GPU"}
 
 
 def cpu_fine_tune(n_rays):
@@ -714,6 +791,15 @@ def main():
         v, cores, sample = cpu_reference(args.config, 4096, 2)
         cpu = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
 
+    tgpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            v, sample = torch_gpu_reference(sc, dev, H, W)
+            tgpu = {"value": v, "unit": "rays/s", "kind": "port", "sample": sample,
+                    "how": "the reference's PyTorch ops (oracle port, fast=True: F.grid_sample, nn.Linear, cumprod) with all tensors on this GPU"}
+        except Exception as e:      # a comparator must never take the bench line down
+            tgpu = {"value": None, "error": f"{type(e).__name__}: {e}"[:300]}
+
     if rank == 0:
         line = {"metric": "rays_per_sec_128_samples", "value": value, "unit": "rays/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -722,7 +808,7 @@ def main():
                 "config": {"workload": args.config + ": " + c["desc"], "rays_per_gpu_per_step": R, "samples_per_ray": S,
                            "l2": "256 MiB buffer written between timed steps (L2 flush); per-step working set 3.6 GB > L2",
                            "parallelism": f"ray-sharded x{world}, one NCCL frame broadcast per step" if world > 1 else "1 GPU"},
-                "steps_ms": [round(x, 3) for x in ms], "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+                "steps_ms": [round(x, 3) for x in ms], "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "torch_gpu_baseline": tgpu,
                 "gather_stage": gstage, "fine_tune": ft, "next_rows": {"f1_ray_builder": f1, "f3_cost_volume": f3, "f4_sf_losses": f4}}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -88,7 +88,7 @@ def project_view(pts, w2c, K, W, H):
     p = pts.reshape(1, -1, 3)
     p = torch.matmul(p, w2c[:, :3, :3].transpose(1, 2)) + w2c[:, :3, 3:].reshape(1, 1, 3)
     q = p @ K.transpose(1, 2)
-    inv_scale = torch.tensor([W - 1, H - 1])
+    inv_scale = torch.tensor([W - 1, H - 1], device=q.device)
     uv = (q[:, :, :2] / q[:, :, -1:] + 0.0) / inv_scale.reshape(1, 1, 2)
     grid = uv.view(pts.shape[:3] + (2,)) * 2.0 - 1.0
     return grid
@@ -177,7 +177,7 @@ def run_mlp(net, x, netchunk=None):
 # --------------------------------------------------------------------------- composite
 def excl_cumprod(x):
     """T_i = prod_{j<i} x_j (`renderer.py:107-108`)."""
-    ones = torch.ones(x.shape[:-1] + (1,), dtype=x.dtype)
+    ones = torch.ones(x.shape[:-1] + (1,), dtype=x.dtype, device=x.device)
     return torch.cumprod(torch.cat([ones, x], -1), -1)[..., :-1]
 
 
