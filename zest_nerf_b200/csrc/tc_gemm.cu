@@ -17,14 +17,20 @@
 // taking the same GemmArgs / fused epilogue (bias, pre-gate copy, gate, ReLU, accumulate, split-K atomics) as the
 // CUDA-core sgemm_kernel it replaces; the exact-fp32 SIMT kernel stays selectable (zest_set_gemm_engine).
 //
-// One CTA = one 128 x (<=256) output tile, 256 threads, 2 CTAs per SM (96 KB smem, 256 TMEM columns each) so one
-// CTA's epilogue overlaps the other's main loop.  Main loop per K stage (32 k as bf16, 16 k as tf32):
-//   all threads: convert the register-prefetched fp32 operand slab -> hi / lo images in the K-major no-swizzle
-//                UMMA layout (core matrix = 8 rows x 16 B; same layout the MLP kernel uses), then issue the next
-//                stage's global loads (vector loads along whichever dimension is contiguous)
-//   thread 0:    6 UMMAs (2 K steps x 3 products), tcgen05.commit -> the stage's "empty" mbarrier
-// Epilogue: tcgen05.ld 32 columns per warp pass (lane = row), per-warp shared-memory transpose, fused ops, then
-// global accesses in which a warp covers 4 rows x 128 contiguous bytes.
+// Two kernels, both with two CTAs per SM (96 KB smem, 256 TMEM columns each: one CTA's epilogue runs under the other's
+// main loop) and K stages of four 16-byte chunks per row and part (32 k as bf16, 16 k as tf32):
+//   tc_gemm_packed_kernel  B is a weight matrix every row tile re-reads (forward, dX): packed once per call into the UMMA
+//                          stage images and streamed by TMA; eight worker warps stage A through registers (static register
+//                          sets, up to 6 stages ahead) and run the epilogue, a ninth warp drives the TMA and issues the
+//                          UMMAs (converged warp, warp-uniform descriptors); mbarriers only in the main loop.
+//                          128 x 256 tiles, or 128 x 128 with separate head / cross accumulators (engine 2).
+//   tc_gemm_kernel         both operands are activations (dW, split-K): all 256 threads stage A and B through registers into
+//                          the K-major no-swizzle images (core matrix = 8 rows x 16 B, the MLP kernel's layout), thread 0
+//                          issues 6 UMMAs per stage (2 K steps x 3 products) and commits to the stage's "empty" mbarrier;
+//                          the bias gradient (row sums of A) rides along in the staging threads.
+// Epilogue (shared): tcgen05.ld 32 columns per warp pass (lane = row), per-warp shared-memory transpose, fused ops (bias,
+// Z copy, gate, ReLU, accumulate, the gate backward of the layer below, vector atomics for split-K), global accesses in
+// which a warp covers 4 rows x 128 contiguous bytes, every load of a row batch issued before its first use.
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
