@@ -24,7 +24,7 @@
  *   zest_sf_smooth_loss_fwd / _bwd        losses.py:142-161 compute_sf_smooth_loss            ("next" row f4)
  *   zest_sf_lke_loss_fwd / _bwd           losses.py:164-203 compute_sf_lke_loss
  *   zest_project_ndc_fwd / _bwd           utils.py:516-539 projection_from_ndc (+ :507-514 NDC2Euclidean)
- *   zest_cost_volume_fwd                  networks.py:1077-1140 MVSNet.build_volume_cost + utils.py:49-99 homo_warp
+ *   zest_cost_volume_fwd / _bwd           networks.py:1077-1140 MVSNet.build_volume_cost + utils.py:49-99 homo_warp
  *                                         ("next" row f3, first half)
  *
  * Conventions
@@ -187,7 +187,7 @@ int zest_project_ndc_bwd(const float* w2c, const float* weights, const float* ra
                          float f, const float* g_pts_2d, float* g_weights, float* g_raw_pts, void* stream);
 
 /* ---- plane-sweep cost volume ("next" row f3, first half) ---------------------------------------------
- * networks.py:1077-1140 MVSNet.build_volume_cost + utils.py:49-99 homo_warp in one pass, forward only.
+ * networks.py:1077-1140 MVSNet.build_volume_cost + utils.py:49-99 homo_warp in one pass.
  * feats_cl [V, C/4, H, W, 4] feature maps as planes of channel quads (view 0 = reference, C % 4 == 0), imgs_cl [V, H, W, 4] the images at
  * feature resolution (r, g, b, 0), proj_host: HOST pointer, (V - 1) x 12 floats = rows of the 3x4 "src_proj @ ref_proj_inv"
  * of every source view, depth [D] plane depths (device).  Outputs (NCDHW, Hp = H + 2 pad, Wp = W + 2 pad):
@@ -195,6 +195,10 @@ int zest_project_ndc_bwd(const float* w2c, const float* weights, const float* ra
  * features over the views; in_masks [V, D, Hp, Wp] = 1 for the reference, -1 < grid < 1 for the source views. */
 int zest_cost_volume_fwd(const float* feats_cl, const float* imgs_cl, const float* proj_host, const float* depth,
                          int V, int C, int H, int W, int D, int pad, float* img_feat, float* in_masks, void* stream);
+/* Backward wrt the feature maps: g_var = gradient of the C variance channels ([C, D, Hp, Wp], i.e. img_feat + 3 V channels),
+ * g_feats_cl [V, C/4, H, W, 4] is ACCUMULATED into (zero it first).  Images, projections and depths are data. */
+int zest_cost_volume_bwd(const float* feats_cl, const float* proj_host, const float* depth, int V, int C, int H, int W,
+                         int D, int pad, const float* g_var, float* g_feats_cl, void* stream);
 
 /* ---- alpha compositing (warp per ray) ---------------------------------------------------- */
 /* raw [R*S, ld_raw] (rgb_raw 3, sigma_raw 1, ...), z [R,S], cos_angle [R], noise [R,S] or NULL

@@ -708,9 +708,8 @@ def test_cost_volume_matches_reference_golden(zops):
     from tests.golden.make_golden_costvol import build_costvol_case
     gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "costvol.npz"))
     case = build_costvol_case()
-    with torch.no_grad():
-        vol, masks = mvs.build_volume_cost(case["imgs"].to(DEV), case["feats"].to(DEV), case["proj_mats"].to(DEV),
-                                           case["depth_values"].to(DEV), pad=case["pad"])
+    vol, masks = mvs.build_volume_cost(case["imgs"].to(DEV), case["feats"].to(DEV), case["proj_mats"].to(DEV),
+                                       case["depth_values"].to(DEV), pad=case["pad"])
     want_vol, want_mask = torch.from_numpy(gold["img_feat"]), torch.from_numpy(gold["in_masks"]).float()
     assert vol.shape == want_vol.shape and masks.shape == want_mask.shape
     mism = float((masks.cpu() != want_mask).float().mean())
@@ -743,3 +742,23 @@ def test_cost_volume_full_size_properties(zops):
     assert float((win[3:6] - win[0:3]).abs().max()) <= 1e-4            # warped image = reference image (grid rounding ~1e-5 px)
     inside = masks[0, 1, 0, pad + 1:H + pad - 1, pad + 1:W + pad - 1]
     assert float(inside.min()) == 1.0 and float(masks[0, 1, 0, 0, 0]) == 0.0
+
+
+def test_cost_volume_gradient_matches_oracle_autograd(zops):
+    """d loss / d feature maps through the plane-sweep variance (zest_cost_volume_bwd: taps recomputed, vector atomics into
+    the feature-map gradient) against autograd through the CPU oracle (itself bit-equal to the reference's build_volume_cost)."""
+    from zest_nerf_b200 import mvs
+    from tests.golden.make_golden_costvol import build_costvol_case
+    case = build_costvol_case()
+    g = torch.Generator().manual_seed(4)
+    f_cpu = case["feats"].clone().requires_grad_(True)
+    vol_o, _ = zo.cost_volume(case["imgs"], f_cpu, case["proj_mats"], case["depth_values"], pad=case["pad"])
+    wts = torch.randn(vol_o.shape, generator=g)
+    (vol_o * wts).sum().backward()
+    f_gpu = case["feats"].clone().to(DEV).requires_grad_(True)
+    vol_c, masks = mvs.build_volume_cost(case["imgs"].to(DEV), f_gpu, case["proj_mats"].to(DEV), case["depth_values"].to(DEV), pad=case["pad"])
+    assert not masks.requires_grad
+    (vol_c * wts.to(DEV)).sum().backward()
+    err = float((f_gpu.grad.cpu() - f_cpu.grad).abs().max()) / float(f_cpu.grad.abs().max())
+    print(f"   cost volume gradient: rel max err {err:.2e} (|g|max {float(f_cpu.grad.abs().max()):.2e})")
+    assert err <= 1e-4

@@ -51,6 +51,7 @@ SIGNATURES = {
     "zest_project_ndc_fwd": (_i, [_p, _p, _p, _l, _i, _i, _i, _f, _p, _p]),
     "zest_project_ndc_bwd": (_i, [_p, _p, _p, _l, _i, _i, _i, _f, _p, _p, _p, _p]),
     "zest_cost_volume_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "zest_cost_volume_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "zest_set_gemm_engine": (_i, [_i]),
     "zest_gemm_f32": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _l, _i, _l, _p, _i, _i, _i, _p, _l, _p]),
     "zest_tc_selftest": (_i, [_p, _p, _p, _i, _i, _i, _p]),

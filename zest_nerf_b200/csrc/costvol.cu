@@ -7,7 +7,8 @@
 // source view (R (x - pad, y - pad, 1) + T / depth, utils.py:77-89), gathers the 4 bilinear corners of the feature map (laid
 // out as planes of channel quads; the maps are a few MB and stay in L1 / L2), keeps sum and sum of
 // squares in registers and writes the image channels, the variance and the in-frustum masks exactly once.
-// HBM-bound on its output: (3 V + C + V) x 4 bytes per voxel.  Forward only (inference: test.py / render_spiral.py).
+// HBM-bound on its output: (3 V + C + V) x 4 bytes per voxel.  The backward (wrt the feature maps) recomputes the taps per
+// voxel and scatters with vector atomics.
 #include "common.cuh"
 
 namespace zest {
@@ -127,6 +128,84 @@ __global__ void __launch_bounds__(256) cost_volume_kernel(const float* __restric
   }
 }
 
+
+// Backward wrt the feature maps (the images, projections and depths are data).  var_c = sq inv - (sum inv)^2 with
+// sum = f_ref + sum_v g_v, sq = f_ref^2 + sum_v g_v^2  =>  d var / d x = 2 inv (x - sum inv) for x in {f_ref, g_v}; g_v is the
+// bilinear tap, so its gradient scatters to the 4 corners with the tap weights.  One thread per voxel recomputes the taps and
+// issues 128-bit vector atomics into the gradient maps (same planes-of-quads layout as the features).
+__device__ __forceinline__ void scatter4(float* __restrict__ base, const Tap& t, float4 g) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (t.off[k] < 0) continue;
+    atomicAdd(reinterpret_cast<float4*>(base + (int64_t)t.off[k] * 4), make_float4(g.x * t.w[k], g.y * t.w[k], g.z * t.w[k], g.w * t.w[k]));
+  }
+}
+
+template <int NSRC>
+__global__ void __launch_bounds__(256) cost_volume_bwd_kernel(const float* __restrict__ feats_cl, Sweep sw, const float* __restrict__ depth,
+                                                              int C, int H, int W, int D, int pad, const float* __restrict__ g_var,
+                                                              float* __restrict__ g_feats_cl) {
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const int64_t plane = (int64_t)Hp * Wp, vol = plane * D;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= vol) return;
+  const int d = (int)(idx / plane);
+  const int rem = (int)(idx - (int64_t)d * plane);
+  const int y = rem / Wp, x = rem - y * Wp;
+  const float gx0 = (float)x - (float)pad, gy0 = (float)y - (float)pad;
+  const float dep = __ldg(depth + d);
+  const bool inside = x >= pad && x < W + pad && y >= pad && y < H + pad;
+  const int ref_off = inside ? (y - pad) * W + (x - pad) : -1;
+  Tap tap[NSRC];
+  float cnt = 1.f;
+#pragma unroll
+  for (int v = 0; v < NSRC; ++v) {
+    float s[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      s[j] = __fadd_rn(dot3(gx0, gy0, 1.f, sw.r[v][3 * j], sw.r[v][3 * j + 1], sw.r[v][3 * j + 2]), __fdiv_rn(sw.t[v][j], dep));
+    const float u = __fdiv_rn(s[0], s[2]), w = __fdiv_rn(s[1], s[2]);
+    const float gx = __fsub_rn(__fdiv_rn(u, (float)(W - 1) / 2.f), 1.f), gy = __fsub_rn(__fdiv_rn(w, (float)(H - 1) / 2.f), 1.f);
+    make_tap(gx, gy, H, W, tap[v]);
+    cnt += tap[v].mask;
+  }
+  const float inv = __fdiv_rn(1.0f, cnt);
+  const int64_t vstride = (int64_t)(C >> 2) * H * W * 4;
+  for (int c = 0; c < C; c += 4) {
+    const float* plane0 = feats_cl + (int64_t)(c >> 2) * H * W * 4;
+    float* gplane0 = g_feats_cl + (int64_t)(c >> 2) * H * W * 4;
+    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (inside) f = __ldg(reinterpret_cast<const float4*>(plane0 + (int64_t)ref_off * 4));
+    float4 g[NSRC];
+    float4 sum = f;
+#pragma unroll
+    for (int v = 0; v < NSRC; ++v) {
+      g[v] = tap4(plane0 + (v + 1) * vstride, 4, tap[v]);
+      sum.x += g[v].x; sum.y += g[v].y; sum.z += g[v].z; sum.w += g[v].w;
+    }
+    const float4 go = make_float4(__ldg(g_var + (int64_t)(c + 0) * vol + idx), __ldg(g_var + (int64_t)(c + 1) * vol + idx),
+                                  __ldg(g_var + (int64_t)(c + 2) * vol + idx), __ldg(g_var + (int64_t)(c + 3) * vol + idx));
+    const float k2 = 2.f * inv;
+    const float4 mean = make_float4(sum.x * inv, sum.y * inv, sum.z * inv, sum.w * inv);
+    if (inside)
+      atomicAdd(reinterpret_cast<float4*>(gplane0 + (int64_t)ref_off * 4),
+                make_float4(k2 * go.x * (f.x - mean.x), k2 * go.y * (f.y - mean.y), k2 * go.z * (f.z - mean.z), k2 * go.w * (f.w - mean.w)));
+#pragma unroll
+    for (int v = 0; v < NSRC; ++v)
+      scatter4(gplane0 + (v + 1) * vstride, tap[v],
+               make_float4(k2 * go.x * (g[v].x - mean.x), k2 * go.y * (g[v].y - mean.y), k2 * go.z * (g[v].z - mean.z), k2 * go.w * (g[v].w - mean.w)));
+  }
+}
+
+static void fill_sweep(Sweep& sw, const float* proj_host, int nsrc) {
+  for (int v = 0; v < nsrc; ++v) {
+    for (int j = 0; j < 3; ++j) {
+      for (int k = 0; k < 3; ++k) sw.r[v][3 * j + k] = proj_host[12 * v + 4 * j + k];
+      sw.t[v][j] = proj_host[12 * v + 4 * j + 3];
+    }
+  }
+}
+
 }  // namespace
 }  // namespace zest
 
@@ -155,6 +234,26 @@ extern "C" int zest_cost_volume_fwd(const float* feats_cl, const float* imgs_cl,
     default:
       set_error("zest_cost_volume_fwd: %d source views not instantiated (1..4)", V - 1);
       return ZEST_E_ARG;
+  }
+  ZEST_LAUNCH_CHECK();
+  return ZEST_OK;
+}
+
+extern "C" int zest_cost_volume_bwd(const float* feats_cl, const float* proj_host, const float* depth, int V, int C, int H, int W, int D,
+                                    int pad, const float* g_var, float* g_feats_cl, void* stream) {
+  ZEST_CHECK_ARG(feats_cl && proj_host && depth && g_var && g_feats_cl, "zest_cost_volume_bwd: null argument");
+  ZEST_CHECK_ARG(V >= 2 && V - 1 <= 4 && C > 0 && (C % 4) == 0 && H > 1 && W > 1 && D > 0 && pad >= 0,
+                 "zest_cost_volume_bwd: unsupported shape (V=%d C=%d H=%d W=%d D=%d pad=%d)", V, C, H, W, D, pad);
+  Sweep sw;
+  fill_sweep(sw, proj_host, V - 1);
+  const int64_t vol = (int64_t)D * (H + 2 * pad) * (W + 2 * pad);
+  const unsigned grid = (unsigned)((vol + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (V - 1) {
+    case 1: cost_volume_bwd_kernel<1><<<grid, 256, 0, st>>>(feats_cl, sw, depth, C, H, W, D, pad, g_var, g_feats_cl); break;
+    case 2: cost_volume_bwd_kernel<2><<<grid, 256, 0, st>>>(feats_cl, sw, depth, C, H, W, D, pad, g_var, g_feats_cl); break;
+    case 3: cost_volume_bwd_kernel<3><<<grid, 256, 0, st>>>(feats_cl, sw, depth, C, H, W, D, pad, g_var, g_feats_cl); break;
+    default: cost_volume_bwd_kernel<4><<<grid, 256, 0, st>>>(feats_cl, sw, depth, C, H, W, D, pad, g_var, g_feats_cl); break;
   }
   ZEST_LAUNCH_CHECK();
   return ZEST_OK;
