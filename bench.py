@@ -524,6 +524,25 @@ def run_reference(args):
     if rank != 0:
         return
     c = CONFIGS[args.config]
+    if args.config == "cfg5":        # the fine-tune step: the oracle's autograd fwd + bwd on the host cores, a bounded batch per step
+        n, rps, res = 256, [], None
+        t_all = time.perf_counter()
+        for step in range(args.warmup + args.steps):
+            res = cpu_fine_tune(n)
+            if step >= args.warmup:
+                rps.append(res["value"])
+            if time.perf_counter() - t_all > 240:
+                break
+        value = sum(rps) / max(1, len(rps))
+        line = {"impl": "reference", "metric": "rays_per_sec_128_samples_fwd_bwd", "value": value, "unit": "rays/s", "n_gpus": args.gpus,
+                "steps": len(rps), "warmup": args.warmup, "ms_per_step": 1e3 * n / value, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "cfg5: " + c["desc"], "rays_per_step": n, "samples_per_ray": S},
+                "cpu_baseline": {"value": value, "unit": "rays/s", "cores": res["cores"], "kind": "port",
+                                 "sample": f"{n}-ray batch per step; oracle port of the reference (same torch CPU ops + autograd)"},
+                "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
     n = 2048
     rps = []
     cores = None
