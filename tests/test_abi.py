@@ -35,6 +35,19 @@ def test_argument_validation_without_gpu(lib):
     assert lib.zest_net_create(7, 63, 20, 27, 256, 8, 4) is None
 
 
+def test_new_entry_points_validate_arguments_without_gpu(lib):
+    """The training-path GEMM hook, the scene-flow reductions and the cost volume reject bad arguments before any CUDA call."""
+    assert lib.zest_gemm_f32(None, 1, 1, None, 1, 1, None, 1, 4, 4, 4, None, 0, 1, 1, None, 0, None) == -1
+    assert b"zest_gemm_f32" in lib.zest_last_error()
+    assert lib.zest_sf_smooth_loss_fwd(None, None, 4, 128, 121, 288, 512, 460.8, None, None) == -1
+    assert lib.zest_sf_lke_loss_fwd(None, None, None, 4, 128, 115, 288, 512, 460.8, None, None) == -1
+    assert lib.zest_project_ndc_fwd(None, None, None, 4, 128, 288, 512, 460.8, None, None) == -1
+    assert lib.zest_cost_volume_fwd(None, None, None, None, 3, 32, 72, 128, 128, 24, None, None, None) == -1
+    assert b"zest_cost_volume_fwd" in lib.zest_last_error()
+    prev = lib.zest_set_gemm_engine(0)          # pure host state: round-trips
+    assert lib.zest_set_gemm_engine(prev) == 0
+
+
 def test_product_path_does_not_import_oracle():
     for root, _, files in os.walk(os.path.join(ROOT, "zest_nerf_b200")):
         for f in files:
