@@ -1,8 +1,10 @@
-// fp32 radiance MLP (CUDA cores): forward and backward of networks.py:150-221 (Renderer.forward, v0).
+// fp32-grade radiance MLP, layer by layer: forward and backward of networks.py:150-221 (Renderer.forward, v0).
 //
 // This is the precision-reference path ("fp32 MLP" of the parity bar: RGB/depth <= 2e-3 max-abs)
 // and the training path (fine_tune.py): it keeps every activation when train=1 so the backward
-// can run layer by layer.  The inference hot path is the bf16 tcgen05 kernel in mlp_tc.cu.
+// can run layer by layer.  Every layer is one GEMM with a fused epilogue (launch_gemm, sgemm.cuh): on the
+// tensor cores with split-precision operands by default (tc_gemm.cu), on CUDA cores in exact fp32 on request
+// (sgemm.cu).  The inference hot path is the bf16 tcgen05 kernel in mlp_tc.cu.
 //
 //   g   = pts_bias(feat)                                   networks.py:174
 //   h_i = relu(L_i(h_{i-1}) * g), i < depth; [pe | h] after layer `skip`   :176-182
@@ -29,7 +31,7 @@ struct F32Plan {
   int W, P, F, Cv, D, skip, ns;
   int ldX5, ldVX;
   int64_t G, X5, H[16], Z[16], VX, V128, SH, RGB;           // forward
-  int64_t gHa, gHb, dZ, gG, gX5, gVX, gV128, gSH, gRGB;      // backward scratch (train only)
+  int64_t gHa, gHb, dZ, gG, gX5, gVX, gV128, gSH, gRGB;      // backward scratch (train only); dZ / gHb ping-pong as dZ_i
   int64_t PACK;                                               // weight-operand stage images of the tensor-core GEMM
   static constexpr int64_t kPackFloats = 512 * 1024;          // 2 MiB >= 2 column tiles x 22 K stages x 32 KiB
   int64_t total;
