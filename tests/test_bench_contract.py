@@ -28,3 +28,14 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_reference_arm_fine_tune_config():
+    """BASELINE config 5 under the same contract: the oracle's autograd step on the host cores."""
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--config", "cfg5"], capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    assert d["impl"] == "reference" and d["metric"] == "rays_per_sec_128_samples_fwd_bwd" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["value"] == d["value"]
