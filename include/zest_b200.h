@@ -92,11 +92,13 @@ int zest_dirfeat_fwd(const float* rays_dir, int64_t R, const float* cam_ref, flo
 
 /* ---- positional encoding + input assembly (fp32 path / module boundary) ------------------ */
 /* x [M, ldx] = [ PE_{nf_pts}(pts[M, c_pts (+ time t appended if has_t)]) | feats[M, F] |
- *               PE_{nf_dir}(dirs[ray of row]) ], ray of row = row / S. */
+ *               PE_{nf_dir}(dirs[ray of row]) ], ray of row = row / S.
+ * has_t: 0 = 3 channels; 1 = 4 channels, the 4th is the constant t (renderer.py:300-318);
+ *        2 = 4 channels read from memory (stand-alone Embedding(4, N).forward, networks.py:48-65). */
 int zest_encode_fwd(const float* ndc, int ndc_ld, int has_t, float t, int nf_pts,
                     const float* feats, int ldf, int F, const float* dirs, int nf_dir, int S,
                     int64_t M, float* x, int ldx, void* stream);
-/* gndc[M, gndc_ld] (+)= d loss / d ndc through PE(pts) given gx[M, ldx] (first 3 channels only). */
+/* gndc[M, gndc_ld] (+)= d loss / d ndc through PE(pts) given gx[M, ldx] (first 3 channels; all 4 when has_t == 2). */
 int zest_encode_bwd(const float* ndc, int ndc_ld, int has_t, float t, int nf_pts, const float* gx,
                     int ldx, int64_t M, float* gndc, int gndc_ld, int accumulate, void* stream);
 

@@ -1,0 +1,162 @@
+"""The reference's OWN callers running unchanged on top of the drop-in ("the strongest
+train.py-calls-it-unchanged check available offline").
+
+`baseline/_ref/` holds the unmodified reference files (vendored by `baseline/vendor_reference.py`, git-ignored, shipped
+with the snapshot).  `baseline.ref_loader.load(patched=True)` imports the reference's `networks.py` with THIS repo's
+`rendering` bound as module `renderer`, so `DyMVSNeRF_G.forward_val`, `DyMVSNeRF_G.forward`
+and `MVSNeRF_G.forward` (networks.py:595-709, 474-581, 355-437) execute their own ray building, chunk loops and dict
+plumbing and call our CUDA path; the same generators imported unpatched (reference `rendering`, stock PyTorch ops on the
+same GPU, same seeds) are the comparison.  The radiance MLPs are the REFERENCE's `MVSNeRF` modules in both arms, i.e. the
+reference's module is what gets passed to our `rendering()`.
+"""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from baseline import ref_loader
+from zest_nerf_b200.synthetic import make_scene
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_loader.available(), reason="baseline/_ref not vendored")]
+DEV = "cuda:0"
+MEAN = torch.tensor([0.485, 0.456, 0.406]).view(1, 1, 3, 1, 1)
+STD = torch.tensor([0.229, 0.224, 0.225]).view(1, 1, 3, 1, 1)
+
+
+class FixedEncoder(torch.nn.Module):
+    """Stands where `MVSNet` stands in the generators (networks.py:513-544): returns a fixed encoding volume, so the test
+    isolates the rendering path (the encoding CNN has its own parity tests)."""
+
+    def __init__(self, vol):
+        super().__init__()
+        self.vol = torch.nn.Parameter(vol.clone())
+
+    def forward(self, imgs, proj_mats, near_far, pad=0, **kw):
+        return self.vol, None, None
+
+
+def _args(sc, **over):
+    a = SimpleNamespace(**vars(sc.args))
+    a.__dict__.update(batch_size=96, N_samples=sc.n_samples, pad=sc.pad, vis_cnn=False, save_test="/tmp", patch_size=-1,
+                      scale_anneal=-1, gan_type=None, with_chain_loss=True, use_motion_mask=False, num_extra_samples=0,
+                      white_bkgd=False, raw_noise_std=1.0, chunk=512, netchunk=512)
+    a.__dict__.update(over)
+    return a
+
+
+def _batch(sc, g):
+    """The batch dict of SURVEY 3.2 (data/nsff.py:369-396), synthetic."""
+    H, W, V = sc.H, sc.W, sc.V
+    proj = torch.eye(4)[:3][None, None].repeat(1, V + 1, 1, 1)
+    x = {"images": (sc.imgs - MEAN) / STD, "proj_mats": proj, "near_fars": sc.near_fars, "w2cs": sc.w2cs, "c2ws": sc.c2ws,
+         "intrinsics": sc.intrinsics, "time": torch.tensor([14.0]), "total_frames": torch.tensor([24.0]),
+         "flow_fwds": torch.randn((1, 1, 2, H, W), generator=g), "flow_bwds": torch.randn((1, 1, 2, H, W), generator=g),
+         "mask_fwds": torch.rand((1, 1, H, W), generator=g), "mask_bwds": torch.rand((1, 1, H, W), generator=g),
+         "depths": torch.rand((1, 1, H, W), generator=g) * 4 + 2, "motion_coords": torch.zeros((1, 8, 2))}
+    if sc.dynamic:
+        x.update({"nb_imgs": (sc.nb_imgs - MEAN) / STD, "nb_proj_mats": proj[:, :4].clone(), "nb_w2cs": sc.nb_cam_mat["w2cs"],
+                  "nb_intr": sc.nb_cam_mat["intrinsics"]})
+    return {k: v.to(DEV) for k, v in x.items()}
+
+
+def _generators(dynamic, **arg_over):
+    """(reference generator, patched generator, batch): identical weights, identical volumes."""
+    ref, pat = ref_loader.load(False), ref_loader.load(True)
+    assert pat.networks.rendering.__module__ == "zest_nerf_b200.renderer" and ref.networks.rendering.__module__ == "renderer"
+    gens = []
+    for mods in (ref, pat):
+        nw = mods.networks
+        # the REFERENCE's MVSNeRF / Embedding classes in both arms (same seed -> identical init)
+        sc = make_scene(H=32, W=40, V=3, pad=4, D=32, dynamic=dynamic, seed=41, spread=3.0, net_cls=nw.MVSNeRF, emb_cls=nw.Embedding)
+        args = _args(sc, **arg_over)
+        if dynamic:
+            gen = nw.DyMVSNeRF_G(args, 30, sc.net_dynamic, sc.net_static, FixedEncoder(sc.vol_static), FixedEncoder(sc.vol_dynamic),
+                                 sc.emb_pts, sc.emb_xyzt, sc.emb_dir)
+        else:
+            gen = nw.MVSNeRF_G(args, sc.net_static, FixedEncoder(sc.vol_static), sc.emb_pts, sc.emb_dir)
+        gens.append(gen.to(DEV))
+    return gens[0], gens[1], _batch(sc, torch.Generator().manual_seed(3))
+
+
+def _seed(s):
+    torch.manual_seed(s)
+    torch.cuda.manual_seed(s)
+
+
+def test_forward_val_runs_unchanged_on_the_drop_in(lib):
+    """`DyMVSNeRF_G.forward_val` (the test.py / validation frame loop): the reference's chunk loop calls our `rendering`
+    once per 512-ray chunk; the six per-chunk map lists and weights_map_dd against the reference's own GPU path."""
+    from zest_nerf_b200 import ops
+    g_ref, g_pat, x = _generators(True)
+    with torch.no_grad():
+        want = g_ref.forward_val(x)
+        with ops.mlp_mode("fp32"):
+            got = g_pat.forward_val(x)
+        with ops.mlp_mode("bf16"):
+            got16 = g_pat.forward_val(x)
+    torch.cuda.synchronize()
+    assert len(got) == len(want) == 8
+    assert torch.equal(got[0], want[0])                       # unpreprocessed images: the caller's own arithmetic
+    names = ("rgbs_blend", "depths_blend", "rgbs_rig", "depths_rig", "rgbs_dy", "depths_dy", "weights_dd")
+    for name, w_list, g_list, h_list in zip(names, want[1:], got[1:], got16[1:]):
+        assert len(w_list) == len(g_list) == 3               # 32 x 40 rays in 512-ray chunks
+        w, g_, h = torch.cat(w_list), torch.cat(g_list), torch.cat(h_list)
+        assert w.shape == g_.shape
+        err = float((g_ - w).abs().max())
+        assert err <= 2e-3, f"{name}: max|err| {err:.3e}"
+        assert float((h - w).abs().max()) <= (3e-2 if "rgb" in name or "weights" in name else 0.15), name
+
+
+@pytest.mark.parametrize("step,chain5", [(0, False), (70000, True)])
+def test_training_forward_and_backward_run_unchanged_on_the_drop_in(lib, step, chain5):
+    """`DyMVSNeRF_G.forward` (train.py's generator step): random pixels + stratified jitter + raw_noise_std = 1.0 drawn by
+    the reference's own code (same CPU / CUDA seeds in both arms), 27 / 28-key dict, then a backward through a fixed
+    projection of the outputs: every parameter of both nets and both encoding volumes against reference autograd."""
+    g_ref, g_pat, x = _generators(True)
+    outs, grads = [], []
+    for gen in (g_ref, g_pat):
+        gen.chain_bwd = False
+        _seed(11)
+        ret = gen(x, step=step)
+        assert ret["chain_5frames"] is chain5 and ret["chain_bwd"] is True
+        pg = torch.Generator().manual_seed(2)
+        loss = 0.0
+        for k in sorted(ret):
+            v = ret[k]
+            if torch.is_tensor(v) and v.requires_grad:
+                loss = loss + (v * torch.randn(v.shape, generator=pg).to(DEV)).sum() / v.numel() ** 0.5
+        loss.backward()
+        outs.append(ret)
+        grads.append({n: p.grad.clone() for n, p in gen.named_parameters() if p.grad is not None})
+    torch.cuda.synchronize()
+    want, got = outs
+    assert set(got) == set(want) and len(want) == (28 if chain5 else 27) + 9
+    for k, v in want.items():
+        if not torch.is_tensor(v):
+            assert got[k] == v or (got[k] is None and v is None), k
+            continue
+        assert got[k].shape == v.shape, k
+        err = float((got[k] - v).abs().max())
+        assert err <= 2e-3, f"{k}: max|err| {err:.3e}"
+    gw, gg = grads
+    assert set(gw) == set(gg) and any("encoding_net.vol" in k for k in gw) and any("nerf_dynamic" in k for k in gw)
+    for k, w in gw.items():
+        l2 = float((gg[k] - w).norm() / (w.norm() + 1e-12))
+        assert l2 <= 5e-3, f"grad {k}: rel L2 {l2:.3e}"
+
+
+def test_static_generator_runs_unchanged_on_the_drop_in(lib):
+    """`MVSNeRF_G.forward` (the static MVSNeRF generator, networks.py:385-437): 7-key dict + target_s / depth_gt / t_vals."""
+    g_ref, g_pat, x = _generators(False)
+    outs = []
+    for gen in (g_ref, g_pat):
+        _seed(5)
+        with torch.no_grad():
+            outs.append(gen(x))
+    want, got = outs
+    assert set(got) == set(want)
+    for k, v in want.items():
+        if v is None:
+            assert got[k] is None
+            continue
+        assert float((got[k] - v).abs().max()) <= 2e-3, k

@@ -30,6 +30,10 @@ void count_launch(int n = 1);
     }                                                                                     \
   } while (0)
 
+#ifndef ZEST_TRY
+#define ZEST_TRY(expr) do { int _r = (expr); if (_r != ZEST_OK) return _r; } while (0)
+#endif
+
 // call after every kernel launch: catches launch-configuration errors without synchronising
 #define ZEST_LAUNCH_CHECK()                                                                \
   do {                                                                                     \

@@ -31,7 +31,7 @@ __global__ void encode_fwd_kernel(const float* __restrict__ ndc, int ndc_ld, int
     float out;
     if (j < c_pe) {
       const int ch = j % C;
-      const float v = (ch == 3) ? t : __ldg(ndc + m * ndc_ld + ch);
+      const float v = (ch == 3 && has_t != 2) ? t : __ldg(ndc + m * ndc_ld + ch);   // has_t == 2: 4th channel from memory
       out = pe_value(v, j / C);
     } else if (j < c_pe + F) {
       out = __ldg(feats + m * ldf + (j - c_pe));
@@ -48,9 +48,10 @@ __global__ void encode_bwd_kernel(const float* __restrict__ ndc, int ndc_ld, int
                                   const float* __restrict__ gx, int ldx, int64_t M, float* gndc, int gndc_ld,
                                   int accumulate) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M * 3) return;
-  const int64_t m = i / 3;
-  const int ch = (int)(i - m * 3);
+  const int nch = has_t == 2 ? 4 : 3;   // a constant time channel (has_t == 1) has no gradient
+  if (i >= M * nch) return;
+  const int64_t m = i / nch;
+  const int ch = (int)(i - m * nch);
   const int C = has_t ? 4 : 3;
   const float v = __ldg(ndc + m * ndc_ld + ch);
   const float* g = gx + m * ldx;
@@ -75,6 +76,7 @@ extern "C" int zest_encode_fwd(const float* ndc, int ndc_ld, int has_t, float t,
   ZEST_CHECK_ARG(ndc && x && M >= 0 && ndc_ld >= 3 && nf_pts >= 0 && nf_pts <= 16 && nf_dir >= 0 && nf_dir <= 16 && S > 0,
                  "zest_encode_fwd: bad arguments");
   ZEST_CHECK_ARG(F == 0 || (feats && ldf >= F), "zest_encode_fwd: bad feats");
+  ZEST_CHECK_ARG(has_t >= 0 && has_t <= 2 && (has_t != 2 || ndc_ld >= 4), "zest_encode_fwd: has_t must be 0, 1 (constant t) or 2 (4th channel in memory)");
   const int width = (has_t ? 4 : 3) * (2 * nf_pts + 1) + F + (dirs ? 3 * (2 * nf_dir + 1) : 0);
   ZEST_CHECK_ARG(ldx >= width, "zest_encode_fwd: ldx %d < row width %d", ldx, width);
   if (M == 0) return ZEST_OK;
@@ -92,8 +94,9 @@ extern "C" int zest_encode_bwd(const float* ndc, int ndc_ld, int has_t, float t,
   (void)t;
   ZEST_CHECK_ARG(ndc && gx && gndc && M >= 0 && ndc_ld >= 3 && gndc_ld >= 3 && nf_pts >= 0 && nf_pts <= 16,
                  "zest_encode_bwd: bad arguments");
+  ZEST_CHECK_ARG(has_t >= 0 && has_t <= 2 && (has_t != 2 || (ndc_ld >= 4 && gndc_ld >= 4)), "zest_encode_bwd: bad has_t / strides");
   if (M == 0) return ZEST_OK;
-  encode_bwd_kernel<<<(unsigned)((M * 3 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ndc, ndc_ld, has_t, nf_pts, gx,
+  encode_bwd_kernel<<<(unsigned)((M * (has_t == 2 ? 4 : 3) + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ndc, ndc_ld, has_t, nf_pts, gx,
                                                                                       ldx, M, gndc, gndc_ld, accumulate);
   ZEST_LAUNCH_CHECK();
   return ZEST_OK;

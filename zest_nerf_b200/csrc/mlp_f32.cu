@@ -116,7 +116,6 @@ static int copy2d(float* dst, int64_t ldd, const float* src, int64_t lds, int co
   return ZEST_OK;
 }
 
-#define ZEST_TRY(expr) do { int _r = (expr); if (_r != ZEST_OK) return _r; } while (0)
 
 // y = x @ W^T + b  with W [J, K] row-major (nn.Linear)
 static GemmArgs linear(const float* x, int64_t ldx, const float* W, int J, int64_t K, const float* b, float* y,
@@ -166,7 +165,7 @@ extern "C" zest_net* zest_net_create(int kind, int in_pts, int in_feat, int in_v
   n->width = width; n->depth = depth; n->skip = skip;
   n->out_ch = kind == 0 ? 4 : (kind == 1 ? 5 : 12);
   n->n_small = kind == 0 ? 1 : (kind == 1 ? 2 : 9);
-  n->packed = false; n->f32 = nullptr; n->tc_blob = nullptr; n->tc_bias = nullptr; n->tc_plan_host = nullptr; n->tc_bytes = 0;
+  n->packed = false; n->f32 = nullptr; n->tc_blob = nullptr; n->tc_bias = nullptr; n->tc_plan_host = nullptr; n->tc_bytes = 0; n->tc_desc_dev = nullptr; n->tc_dirty = true;
   // blob layout; the stacked small heads keep alpha first so column 0 of SH is sigma
   int64_t o = 0;
   int pi = 0;
@@ -222,7 +221,7 @@ extern "C" int zest_net_pack(zest_net* net, const float* const* params, int n_pa
     ZEST_CUDA(cudaMemcpyAsync(net->f32 + net->param_off[i], params[i], (size_t)net->param_numel[i] * sizeof(float),
                               cudaMemcpyDeviceToDevice, st));
   }
-  ZEST_TRY(tc_pack(net, st));
+  net->tc_dirty = true;   // the bf16 tensor-core image is rebuilt by the next inference launch (mlp_tc.cu), not here
   net->packed = true;
   return ZEST_OK;
 }

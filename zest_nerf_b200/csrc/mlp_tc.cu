@@ -86,7 +86,7 @@ struct PackDesc {  // how to build one weight block image from the fp32 blob
 
 struct TcPlanHost {
   std::vector<TcStage> stages;
-  int n_stages = 0;
+  int n_stages = 0, n_packs = 0;
   int P, Ppad, F, Fpad, C, overlap, gate_fp32, cluster2;
   size_t smem_bytes;
 };
@@ -882,6 +882,8 @@ static inline int up(int v, int m) { return (v + m - 1) / m * m; }
 void tc_free(zest_net* net) {
   if (net->tc_blob) cudaFree(net->tc_blob);
   if (net->tc_bias) cudaFree(net->tc_bias);
+  if (net->tc_desc_dev) cudaFree(net->tc_desc_dev);
+  net->tc_desc_dev = nullptr;
   if (net->tc_plan_host) delete (TcPlanHost*)net->tc_plan_host;
   net->tc_blob = nullptr; net->tc_bias = nullptr; net->tc_plan_host = nullptr;
 }
@@ -906,6 +908,7 @@ int tc_pack(zest_net* net, cudaStream_t st) {
   // S = [PE | dirPE x 2 (4 + 4 chunks) | ones (2) | feats] + ring
   ph->smem_bytes = (size_t)(Ppad / 8 + 10 + Fpad / 8) * kChunkBytes + (kBiasInMma ? 0 : (size_t)kBiasOps * 1024) + (size_t)kStages * kStageBytes;
 
+  if (first) {   // the stage plan and the pack descriptors depend on the architecture only: built and uploaded once
   std::vector<TcStage> stages;
   std::vector<PackDesc> packs;
   int64_t blob_off = 0;
@@ -943,10 +946,12 @@ int tc_pack(zest_net* net, cudaStream_t st) {
   for (auto& s : stages) ZEST_CHECK_ARG(s.bytes <= (uint32_t)kStageBytes && (s.bytes & 15u) == 0, "tc_pack: stage of %u bytes", s.bytes);
   ph->stages = stages; ph->n_stages = (int)stages.size();
 
-  if (first) {
     ZEST_CUDA(cudaMalloc(&net->tc_blob, (size_t)blob_off));
     ZEST_CUDA(cudaMalloc(&net->tc_bias, (size_t)kBiasOps * 256 * sizeof(float)));
+    ZEST_CUDA(cudaMalloc(&net->tc_desc_dev, packs.size() * sizeof(PackDesc)));
+    ZEST_CUDA(cudaMemcpy(net->tc_desc_dev, packs.data(), packs.size() * sizeof(PackDesc), cudaMemcpyHostToDevice));
     net->tc_bytes = blob_off;
+    ph->n_packs = (int)packs.size();
   }
   {   // epilogue-side bias table: GATE, L0..L7, FEAT (256 each), VIEWS (128)
     ZEST_CUDA(cudaMemsetAsync(net->tc_bias, 0, (size_t)kBiasOps * 256 * sizeof(float), st));
@@ -958,14 +963,10 @@ int tc_pack(zest_net* net, cudaStream_t st) {
     ZEST_CUDA(put(9, net->b_feat, W));
     ZEST_CUDA(put(10, net->b_views, W / 2));
   }
-  // device-side scratch for the descriptors (freed after the pack kernel is enqueued + synced)
-  PackDesc* d_packs = nullptr;
-  ZEST_CUDA(cudaMalloc(&d_packs, packs.size() * sizeof(PackDesc)));
-  ZEST_CUDA(cudaMemcpyAsync(d_packs, packs.data(), packs.size() * sizeof(PackDesc), cudaMemcpyHostToDevice, st));
-  tc_pack_kernel<<<(unsigned)packs.size(), 256, 0, st>>>(net->f32, d_packs, (uint8_t*)net->tc_blob);
+  // refresh of the weight image: stream-ordered, no allocation, no host synchronisation (capturable in a CUDA graph)
+  tc_pack_kernel<<<(unsigned)ph->n_packs, 256, 0, st>>>(net->f32, (const PackDesc*)net->tc_desc_dev, (uint8_t*)net->tc_blob);
   ZEST_LAUNCH_CHECK();
-  ZEST_CUDA(cudaStreamSynchronize(st));  // host vector / scratch are released below
-  cudaFree(d_packs);
+  net->tc_dirty = false;
   return ZEST_OK;
 }
 
@@ -974,6 +975,11 @@ static unsigned long long* g_timeline = nullptr;
 static int tc_launch(const zest_net* net, TcParams& p, cudaStream_t st) {
   p.tl = g_timeline;
   if (!net->packed) { set_error("zest_mlp_fwd_tc: net not packed"); return ZEST_E_STATE; }
+  if (tc_supported(net) && (net->tc_dirty || !net->tc_plan_host)) {
+    // the bf16 weight image is rebuilt lazily, on the launch stream, the first time an inference launch follows a
+    // zest_net_pack(): fine-tuning (which never reads it) pays nothing per optimiser step
+    ZEST_TRY(tc_pack(const_cast<zest_net*>(net), st));
+  }
   if (!tc_supported(net) || !net->tc_plan_host) {
     set_error("zest_mlp_fwd_tc: the tensor-core path supports width=256 depth=8 skip=4 in_pts in {63,84} in_feat<=64 in_views=27 "
               "(got width=%d depth=%d skip=%d in_pts=%d in_feat=%d in_views=%d); use the fp32 path",

@@ -29,6 +29,8 @@ struct zest_net {
   int64_t tc_bytes;
   float* tc_bias;      // device: [11][256] fp32 biases of the 256-wide ops, read by the tensor-core kernel's epilogue
   void* tc_plan_host;  // host: layer plan (opaque to everything but mlp_tc.cu)
+  void* tc_desc_dev;   // device: pack descriptors (uploaded once)
+  bool tc_dirty;       // f32 changed since the bf16 image was built: rebuilt lazily by the next tensor-core launch
 };
 
 namespace zest {

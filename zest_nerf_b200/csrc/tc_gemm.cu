@@ -663,11 +663,8 @@ __global__ void __launch_bounds__(kWorkers + 32, 2) tc_gemm_packed_kernel(GemmAr
 
 template <int KCH, bool AKC, bool DUAL>
 int launch_packed_variant(const GemmArgs& a, dim3 grid, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    ZEST_CUDA(cudaFuncSetAttribute(tc_gemm_packed_kernel<KCH, AKC, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
-    configured = true;
-  }
+  // the attribute is per device: set it on every launch (a few hundred ns) rather than once per process
+  ZEST_CUDA(cudaFuncSetAttribute(tc_gemm_packed_kernel<KCH, AKC, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
   tc_gemm_packed_kernel<KCH, AKC, DUAL><<<grid, kWorkers + 32, kSmem, st>>>(a, (const uint8_t*)a.b_scratch);
   ZEST_LAUNCH_CHECK();
   return ZEST_OK;
@@ -695,11 +692,7 @@ int launch_packed(const GemmArgs& a, cudaStream_t st) {
 
 template <int KCH, bool AKC, bool BKC>
 int launch_variant(const GemmArgs& a, dim3 grid, int64_t kper, cudaStream_t st) {
-  static bool configured = false;   // per instantiation
-  if (!configured) {
-    ZEST_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<KCH, AKC, BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
-    configured = true;
-  }
+  ZEST_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<KCH, AKC, BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
   tc_gemm_kernel<KCH, AKC, BKC><<<grid, kThreads, kSmem, st>>>(a, kper);
   ZEST_LAUNCH_CHECK();
   return ZEST_OK;

@@ -260,6 +260,17 @@ class PackedNet:
         _lib.check(_lib.load().zest_net_pack(self.handle, arr, len(keep), _stream()), "zest_net_pack")
         self.state = state
 
+    # the handle is process- and module-local: copies / pickles of the owning module must not share it (two modules
+    # repacking different weights into one zest_net, double free) - a copy starts without one and is rebuilt lazily
+    def __deepcopy__(self, memo):
+        return None
+
+    def __copy__(self):
+        return None
+
+    def __reduce__(self):
+        return (_no_packed_net, ())
+
     def __del__(self):
         try:
             if getattr(self, "handle", None):
@@ -267,6 +278,10 @@ class PackedNet:
                 self.handle = None
         except Exception:
             pass
+
+
+def _no_packed_net():
+    return None
 
 
 def packed(net):
@@ -530,14 +545,40 @@ def renderer_forward(nerf, x):
     return raw.reshape(*lead, pk.out_ch)
 
 
+class EmbedFn(torch.autograd.Function):
+    """`Embedding.forward` (networks.py:48-65) for 3- or 4-channel inputs; d/dx through the PE backward kernel."""
+
+    @staticmethod
+    def forward(ctx, x, n_freqs):
+        Cc = x.shape[-1]
+        flat = _f32c(x.detach().reshape(-1, Cc), "x")
+        M = flat.shape[0]
+        width = Cc * (2 * n_freqs + 1)
+        out = torch.empty((M, width), device=flat.device, dtype=torch.float32)
+        _lib.check(_lib.load().zest_encode_fwd(_ptr(flat), Cc, 2 if Cc == 4 else 0, 0.0, n_freqs, None, 0, 0, None, 0, 1, M,
+                                               _ptr(out), width, _stream()), "zest_encode_fwd")
+        ctx.save_for_backward(flat)
+        ctx.meta = (n_freqs, tuple(x.shape))
+        return out.reshape(*x.shape[:-1], width)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (flat,) = ctx.saved_tensors
+        n_freqs, xshape = ctx.meta
+        Cc = flat.shape[1]
+        g = _f32c(gout.reshape(flat.shape[0], -1), "grad")
+        gx = torch.empty_like(flat)
+        _lib.check(_lib.load().zest_encode_bwd(_ptr(flat), Cc, 2 if Cc == 4 else 0, 0.0, n_freqs, _ptr(g), g.shape[1], flat.shape[0],
+                                               _ptr(gx), Cc, 0, _stream()), "zest_encode_bwd")
+        return gx.reshape(xshape), None
+
+
 def embed(emb, x):
-    """`Embedding.forward` (networks.py:48-65) through the CUDA encode kernel (no autograd)."""
+    """`Embedding.forward` (networks.py:48-65) through the CUDA encode kernel (3 or 4 input channels, differentiable)."""
     if not emb.logscale:
         raise RuntimeError("only logscale=True embeddings are supported")
-    if emb.in_channels not in (3, 4):
-        raise RuntimeError("Embedding in_channels must be 3 or 4")
-    flat = _f32c(x.reshape(-1, emb.in_channels), "x")
-    if emb.in_channels == 4:
-        raise RuntimeError("standalone 4-channel embedding is fused inside rendering(); call rendering() instead")
-    out = encode_fwd(flat, None, emb.N_freqs, None, None, 0, 1)
-    return out.reshape(*x.shape[:-1], emb.out_channels)
+    if emb.in_channels not in (3, 4) or x.shape[-1] != emb.in_channels:
+        raise RuntimeError(f"Embedding in_channels must be 3 or 4 and match x.shape[-1] (got {emb.in_channels}, x {tuple(x.shape)})")
+    if not x.is_cuda:
+        raise RuntimeError("x must be a CUDA tensor: zest_nerf_b200 has no CPU path")
+    return EmbedFn.apply(x, int(emb.N_freqs))
