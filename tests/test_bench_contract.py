@@ -1,9 +1,14 @@
-"""CPU test of the bench.py contract: the reference arm (`--impl reference`: the CPU oracle port of the reference's
-path, the only part of bench.py that runs without a GPU) prints one JSON line with the agreed keys."""
+"""CPU test of the bench.py contract: the reference arm (`--impl reference`: the unmodified reference from
+`baseline/_ref` when vendored, else the CPU oracle port - the only part of bench.py that runs without a GPU) prints one
+JSON line with the agreed keys."""
 import json
 import os
 import subprocess
 import sys
+
+from baseline import ref_loader
+
+KIND = "reference" if ref_loader.available() else "port"
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -18,7 +23,7 @@ def test_reference_arm_prints_the_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "rays_per_sec_128_samples" and d["unit"] == "rays/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == KIND and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
 
@@ -38,4 +43,4 @@ def test_reference_arm_fine_tune_config():
     assert out.returncode == 0, out.stderr[-2000:]
     d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
     assert d["impl"] == "reference" and d["metric"] == "rays_per_sec_128_samples_fwd_bwd" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == KIND and d["e2e"]["value"] == d["value"]

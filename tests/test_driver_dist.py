@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from zest_nerf_b200.driver import FrameRenderer, slab_bounds
+from zest_nerf_b200.driver import FrameLayout, FrameRenderer, slab_bounds
 
 
 def test_slab_bounds_partition_the_frame():
@@ -38,8 +38,16 @@ def _worker(rank, world, port, n_rays):
         full_rgb = torch.arange(n_rays * 3, dtype=torch.float32).view(1, n_rays, 3)
         full_d = torch.arange(n_rays, dtype=torch.float32).view(1, n_rays) * 0.5
         maps = {"rgb_map": full_rgb[:, r0:r1].clone(), "depth_map": full_d[:, r0:r1].clone()}
-        out = fr.gather_maps(maps, n_rays)
+        out = fr.gather_maps(maps, n_rays, keys=["rgb_map", "depth_map"])
         assert torch.equal(out["rgb_map"], full_rgb) and torch.equal(out["depth_map"], full_d)
+        assert out["_packed"].shape == (n_rays, 4)
+        # a rank with an empty slab (small frame) still takes part in the collective: no hang, right answer
+        small = 100
+        s0, s1 = slab_bounds(small, world, rank)
+        assert (s1 - s0 == 0) == (rank == 1)
+        maps_small = {"rgb_map": full_rgb[:, s0:s1].clone(), "depth_map": full_d[:, s0:s1].clone()}
+        out = fr.gather_maps(maps_small, small, keys=["rgb_map", "depth_map"])
+        assert torch.equal(out["rgb_map"], full_rgb[:, :small]) and torch.equal(out["depth_map"], full_d[:, :small])
         # per-frame broadcast: rank 0 owns the data, the others receive it
         t = torch.full((4, 5), 7.0) if rank == 0 else torch.zeros((4, 5))
         dist.broadcast(t, src=0)
@@ -51,3 +59,19 @@ def _worker(rank, world, port, n_rays):
 def test_two_rank_gather_and_broadcast_gloo():
     port = _free_port()
     mp.spawn(_worker, args=(2, port, 1000), nprocs=2, join=True)
+
+
+def test_frame_layout_packs_every_tensor_once():
+    """The flat frame slot: aligned, non-overlapping views of the shapes the kernels read."""
+    L = FrameLayout(D=16, Hv=10, Wv=12, V=3, H=8, W=9, NB=4, n_cam=4)
+    flat = torch.zeros((L.numel,))
+    v = L.views(flat)
+    assert v["vol_s"].shape == (16, 10, 12, 8) and v["vol_d"].shape == (16, 10, 12, 8)
+    assert v["img"].shape == (3, 8, 9, 4) and v["nb"].shape == (4, 8, 9, 4)
+    assert v["cams_s"].shape == (3, 24) and v["cams_d"].shape == (4, 24) and v["w2cs"].shape == (1, 4, 4, 4)
+    for i, t in enumerate(v.values()):
+        t.fill_(float(i + 1))
+    total = sum((i + 1.0) * t.numel() for i, t in enumerate(v.values()))
+    assert float(flat.sum()) == total                      # no overlap
+    assert all(o % 64 == 0 for o, _, _ in L.items.values())
+    assert FrameLayout(16, 10, 12, 3, 8, 9).key() != L.key() and "vol_d" not in FrameLayout(16, 10, 12, 3, 8, 9).items

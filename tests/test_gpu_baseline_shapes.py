@@ -102,11 +102,14 @@ def test_headline_shapes_match_oracle(zops, name):
 
 def test_bf16_psnr_delta_against_ground_truth_level_target(zops):
     """north_star: PSNR delta under the bf16 MLP <= 0.05 dB.  A PSNR needs a ground truth the model does not reproduce
-    exactly: the target is the ORACLE's fp32 render of an opaque scene (alpha bias + 3: real content, dense weights) plus a
-    fixed perturbation that puts the fp32 model at 30 dB - the quality level of a trained NSFF model - so the delta
-    measures what the bf16 error adds on top of a realistic model error.  Also reported: bf16 vs oracle PSNR itself."""
+    exactly: the target is the ORACLE's fp32 render of an opaque scene (alpha bias + 3, contrast-boosted colour head:
+    real content, dense weights) plus a fixed perturbation that puts the fp32 model at 30 dB - the quality level of a
+    trained NSFF model - so the delta measures what the bf16 error adds on top of a realistic model error.  Also reported: bf16 vs oracle PSNR itself."""
     from zest_nerf_b200.renderer import rendering
     sc, intr, Ht, Wt = _scene("cfg2", opaque=True)
+    with torch.no_grad():      # random-init colour heads are nearly grey: x 8 gives the image real contrast (std ~ 0.06 - 0.1)
+        sc.net_static.nerf.rgb_linear.weight *= 8.0
+        sc.net_dynamic.nerf.rgb_linear.weight *= 8.0
     chunks = _chunks(sc, intr, Ht, Wt, chunk=1024, n=4)
     keys = ("rgb_map", "rgb_map_ref")
     want = {k: [] for k in keys}
@@ -116,7 +119,7 @@ def test_bf16_psnr_delta_against_ground_truth_level_target(zops):
             for k in keys:
                 want[k].append(ref[k][0])
     want = {k: torch.cat(v) for k, v in want.items()}
-    assert float(want["rgb_map_ref"].std()) > 0.02, "the opaque scene must have real content"
+    assert float(want["rgb_map_ref"].std()) > 0.04, "the opaque scene must have real content"
     sc.to(DEV)
     got = {m: {k: [] for k in keys} for m in ("fp32", "bf16")}
     with torch.no_grad():
