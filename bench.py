@@ -709,6 +709,7 @@ def main():
         stage_ev = []
         barrier()
         timed.launches = lib.zest_launch_count()
+        t_host = time.perf_counter()
         for k in range(steps):
             big.zero_()
             timers = [] if with_timers else None
@@ -717,6 +718,7 @@ def main():
             ev[k][1].record()
             stage_ev.append(timers)
         timed.launches = lib.zest_launch_count() - timed.launches
+        timed.host_ms = (time.perf_counter() - t_host) * 1e3 / steps      # host time to ENQUEUE one step (no synchronisation inside)
         barrier()
         ms = [a.elapsed_time(b) for a, b in ev]
         tot = torch.tensor([sum(ms)], device=dev, dtype=torch.float64)
@@ -777,6 +779,7 @@ def main():
     # ---------------- timed region: K steps, CUDA events, L2 flushed between steps ----------------
     total_ms, ms, stage_ev = timed(job.step, args.steps, args.warmup, with_timers=True)
     launches = timed.launches          # this rank's kernels inside the timed steps (libzest_b200 launches only)
+    host_enqueue_ms = timed.host_ms
     out = job.step()
     # the sharded frame must equal the same frame rendered by one GPU alone, bit for bit (rank 0 renders it once, untimed)
     sharded_ok = None
@@ -1030,7 +1033,7 @@ def main():
                 "config": {"workload": args.config + ": " + c["desc"], "rays_per_step": R, "rays_per_gpu_per_step": job.r1 - job.r0, "samples_per_ray": S,
                            "l2": "256 MiB buffer written between timed steps (L2 flush); per-step working set > L2",
                            "parallelism": par},
-                "steps_ms": [round(x, 3) for x in ms], "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "e2e": e2e,
+                "steps_ms": [round(x, 3) for x in ms], "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 3), "clocks": clocks, "roofline": roofline, "e2e": e2e,
                 "cpu_baseline": cpu, "parity": parity, "torch_gpu_baseline": tgpu, "sharded_frame_equals_single_gpu": sharded_ok,
                 "pose_parallel_weak": pose_parallel, "cfg3_strong": cfg3_strong,
                 "gather_stage": gstage, "fine_tune": ft, "next_rows": {"f1_ray_builder": f1, "f3_cost_volume": f3, "f4_sf_losses": f4}}

@@ -14,11 +14,7 @@
 namespace zest {
 namespace {
 
-constexpr int kMaxSrc = 7;   // source views besides the reference
-
-struct Sweep {
-  float r[kMaxSrc][9], t[kMaxSrc][3];
-};
+constexpr int kMaxSrc = 9;   // source views besides the reference (num_keyframes = 10)
 
 struct Tap {              // bilinear footprint of one voxel in one source view (zeros padding, align_corners=True)
   int off[4];             // pixel offsets (y * W + x) of nw, ne, sw, se; -1 = outside
@@ -53,14 +49,40 @@ __device__ __forceinline__ float4 tap4(const float* __restrict__ base, int strid
   return o;
 }
 
+// proj [V - 1][12] (device): rows of src_proj @ ref_proj_inv, staged once per block
+__device__ __forceinline__ void load_proj(const float* __restrict__ proj, int nsrc, float* s_proj) {
+  for (int i = threadIdx.x; i < nsrc * 12; i += blockDim.x) s_proj[i] = __ldg(proj + i);
+  __syncthreads();
+}
+
+// utils.py:77-89: src = R (x, y, 1) + T / depth; uv = src.xy / src.z; grid = uv / ((size - 1) / 2) - 1
+__device__ __forceinline__ void sweep_tap(const float* __restrict__ pm, float gx0, float gy0, float dep, int H, int W, Tap& t) {
+  float s[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    s[j] = __fadd_rn(dot3(gx0, gy0, 1.f, pm[4 * j], pm[4 * j + 1], pm[4 * j + 2]), __fdiv_rn(pm[4 * j + 3], dep));
+  const float u = __fdiv_rn(s[0], s[2]), w = __fdiv_rn(s[1], s[2]);
+  const float gx = __fsub_rn(__fdiv_rn(u, (float)(W - 1) / 2.f), 1.f), gy = __fsub_rn(__fdiv_rn(w, (float)(H - 1) / 2.f), 1.f);
+  make_tap(gx, gy, H, W, t);
+}
+
 // feats_cl [V, C / 4, H, W, 4]: channel quads as planes of float4 pixels - the 32 lanes of a warp (x-adjacent voxels) then read
 // 32 neighbouring float4 of one plane (4 lines) instead of one float4 out of 32 different 128-byte pixels.
-// imgs_cl [V, H, W, 4] (r, g, b, 0) at feature resolution, depth [D]
-// img_feat [3 V + C, D, Hp, Wp], in_masks [V, D, Hp, Wp]
-template <int NSRC>
-__global__ void __launch_bounds__(256) cost_volume_kernel(const float* __restrict__ feats_cl, const float* __restrict__ imgs_cl, Sweep sw,
-                                                          const float* __restrict__ depth, int C, int H, int W, int D, int pad,
-                                                          float* __restrict__ img_feat, float* __restrict__ in_masks) {
+// imgs_cl [V, H, W, 4] (r, g, b, 0) at feature resolution, depth [D].
+// Output, 9 + C channels whatever V is (networks.py:1101: `torch.empty((B, 9 + 32, ...))`; the warped images of source
+// views beyond the second land in channels >= 9 and are overwritten by the variance, `:1138`):
+//   CL = false: img_feat [9 + C, D, Hp, Wp] (the reference's layout), in_masks [V, D, Hp, Wp]
+//   CL = true:  img_feat [D, Hp, Wp, cpad] channels-last (cpad >= 9 + C, pad channels zero) for the 3-D CNN, 128-bit stores
+// The views are walked one after the other with the running sum / sum of squares of all C channels in registers, so any
+// number of source views costs the same registers (num_keyframes = 10 -> 9 source views).
+template <int CQ, bool CL>
+__global__ void __launch_bounds__(256) cost_volume_kernel(const float* __restrict__ feats_cl, const float* __restrict__ imgs_cl,
+                                                          const float* __restrict__ proj, const float* __restrict__ depth, int nsrc,
+                                                          int H, int W, int D, int pad, int cpad, float* __restrict__ img_feat,
+                                                          float* __restrict__ in_masks) {
+  __shared__ float s_proj[kMaxSrc * 12];
+  load_proj(proj, nsrc, s_proj);
+  constexpr int C = 4 * CQ;
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
   const int64_t plane = (int64_t)Hp * Wp, vol = plane * D;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -73,61 +95,70 @@ __global__ void __launch_bounds__(256) cost_volume_kernel(const float* __restric
   const float dep = __ldg(depth + d);
   const bool inside = x >= pad && x < W + pad && y >= pad && y < H + pad;     // F.pad(ref_feats, pad) is zero outside
   const int ref_off = inside ? (y - pad) * W + (x - pad) : -1;
+  const int64_t vstride = (int64_t)CQ * H * W * 4;
 
-  Tap tap[NSRC];
-  float cnt = 1.f;
+  float4 sum[CQ], sq[CQ];
 #pragma unroll
-  for (int v = 0; v < NSRC; ++v) {
-    // utils.py:77-89: src = R (x, y, 1) + T / depth; uv = src.xy / src.z; grid = uv / ((size - 1) / 2) - 1
-    float s[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-      s[j] = __fadd_rn(dot3(gx0, gy0, 1.f, sw.r[v][3 * j], sw.r[v][3 * j + 1], sw.r[v][3 * j + 2]), __fdiv_rn(sw.t[v][j], dep));
-    const float u = __fdiv_rn(s[0], s[2]), w = __fdiv_rn(s[1], s[2]);
-    const float gx = __fsub_rn(__fdiv_rn(u, (float)(W - 1) / 2.f), 1.f), gy = __fsub_rn(__fdiv_rn(w, (float)(H - 1) / 2.f), 1.f);
-    make_tap(gx, gy, H, W, tap[v]);
-    in_masks[(int64_t)(v + 1) * vol + idx] = tap[v].mask;
-    cnt += tap[v].mask;
-  }
-  in_masks[idx] = 1.f;
-  const float inv = __fdiv_rn(1.0f, cnt);     // networks.py:1137
-
-  // image channels: reference view (zero outside the unpadded window; the reference leaves that border uninitialised,
-  // networks.py:1101-1103), then every warped source view
-  {
-    float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (inside) c0 = __ldg(reinterpret_cast<const float4*>(imgs_cl + (int64_t)ref_off * 4));
-    img_feat[0 * vol + idx] = c0.x; img_feat[1 * vol + idx] = c0.y; img_feat[2 * vol + idx] = c0.z;
-#pragma unroll
-    for (int v = 0; v < NSRC; ++v) {
-      const float4 cv = tap4(imgs_cl + (int64_t)(v + 1) * H * W * 4, 4, tap[v]);
-      img_feat[(int64_t)(3 * (v + 1) + 0) * vol + idx] = cv.x;
-      img_feat[(int64_t)(3 * (v + 1) + 1) * vol + idx] = cv.y;
-      img_feat[(int64_t)(3 * (v + 1) + 2) * vol + idx] = cv.z;
-    }
-  }
-  // variance of the feature channels over the views (networks.py:1105-1138)
-  float* var = img_feat + (int64_t)3 * (NSRC + 1) * vol + idx;
-  for (int c = 0; c < C; c += 4) {
+  for (int q = 0; q < CQ; ++q) {
     float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* plane0 = feats_cl + (int64_t)(c >> 2) * H * W * 4;          // view 0, channel quad c / 4
-    const int64_t vstride = (int64_t)(C >> 2) * H * W * 4;
-    if (inside) f = __ldg(reinterpret_cast<const float4*>(plane0 + (int64_t)ref_off * 4));
-    float4 sum = f, sq = make_float4(f.x * f.x, f.y * f.y, f.z * f.z, f.w * f.w);
-#pragma unroll
-    for (int v = 0; v < NSRC; ++v) {
-      const float4 g = tap4(plane0 + (v + 1) * vstride, 4, tap[v]);
-      sum.x += g.x; sum.y += g.y; sum.z += g.z; sum.w += g.w;
-      sq.x += g.x * g.x; sq.y += g.y * g.y; sq.z += g.z * g.z; sq.w += g.w * g.w;
+    if (inside) f = __ldg(reinterpret_cast<const float4*>(feats_cl + (int64_t)q * H * W * 4 + (int64_t)ref_off * 4));
+    sum[q] = f; sq[q] = make_float4(f.x * f.x, f.y * f.y, f.z * f.z, f.w * f.w);
+  }
+  // image channels: reference view (zero outside the unpadded window; the reference leaves that border uninitialised,
+  // networks.py:1101-1103), then the first two warped source views
+  float img9[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (inside) {
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(imgs_cl + (int64_t)ref_off * 4));
+    img9[0] = c0.x; img9[1] = c0.y; img9[2] = c0.z;
+  }
+  float cnt = 1.f;
+  if (!CL && in_masks) in_masks[idx] = 1.f;
+  for (int v = 0; v < nsrc; ++v) {
+    Tap tap;
+    sweep_tap(s_proj + 12 * v, gx0, gy0, dep, H, W, tap);
+    cnt += tap.mask;
+    if (!CL && in_masks) in_masks[(int64_t)(v + 1) * vol + idx] = tap.mask;
+    if (v < 2) {
+      const float4 cv = tap4(imgs_cl + (int64_t)(v + 1) * H * W * 4, 4, tap);
+      img9[3 * v + 3] = cv.x; img9[3 * v + 4] = cv.y; img9[3 * v + 5] = cv.z;
     }
-    const float mx = sum.x * inv, my = sum.y * inv, mz = sum.z * inv, mw = sum.w * inv;
-    var[(int64_t)(c + 0) * vol] = __fsub_rn(__fmul_rn(sq.x, inv), __fmul_rn(mx, mx));
-    var[(int64_t)(c + 1) * vol] = __fsub_rn(__fmul_rn(sq.y, inv), __fmul_rn(my, my));
-    var[(int64_t)(c + 2) * vol] = __fsub_rn(__fmul_rn(sq.z, inv), __fmul_rn(mz, mz));
-    var[(int64_t)(c + 3) * vol] = __fsub_rn(__fmul_rn(sq.w, inv), __fmul_rn(mw, mw));
+    const float* fv = feats_cl + (int64_t)(v + 1) * vstride;
+#pragma unroll
+    for (int q = 0; q < CQ; ++q) {
+      const float4 g = tap4(fv + (int64_t)q * H * W * 4, 4, tap);
+      sum[q].x += g.x; sum[q].y += g.y; sum[q].z += g.z; sum[q].w += g.w;
+      sq[q].x += g.x * g.x; sq[q].y += g.y * g.y; sq[q].z += g.z * g.z; sq[q].w += g.w * g.w;
+    }
+  }
+  const float inv = __fdiv_rn(1.0f, cnt);     // networks.py:1137
+  // variance of the feature channels over the views (networks.py:1105-1138)
+  float var[C];
+#pragma unroll
+  for (int q = 0; q < CQ; ++q) {
+    const float mx = sum[q].x * inv, my = sum[q].y * inv, mz = sum[q].z * inv, mw = sum[q].w * inv;
+    var[4 * q + 0] = __fsub_rn(__fmul_rn(sq[q].x, inv), __fmul_rn(mx, mx));
+    var[4 * q + 1] = __fsub_rn(__fmul_rn(sq[q].y, inv), __fmul_rn(my, my));
+    var[4 * q + 2] = __fsub_rn(__fmul_rn(sq[q].z, inv), __fmul_rn(mz, mz));
+    var[4 * q + 3] = __fsub_rn(__fmul_rn(sq[q].w, inv), __fmul_rn(mw, mw));
+  }
+  if (CL) {
+    float4* o = reinterpret_cast<float4*>(img_feat + idx * cpad);
+    float row[12 + C];     // [9 image channels | C variances | zero pad], written as cpad / 4 vectors
+#pragma unroll
+    for (int i = 0; i < 9; ++i) row[i] = img9[i];
+#pragma unroll
+    for (int i = 0; i < C; ++i) row[9 + i] = var[i];
+    row[9 + C] = 0.f; row[10 + C] = 0.f; row[11 + C] = 0.f;
+#pragma unroll
+    for (int i = 0; i < (12 + C) / 4; ++i)
+      if (4 * i < cpad) o[i] = make_float4(row[4 * i], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) img_feat[(int64_t)i * vol + idx] = img9[i];
+#pragma unroll
+    for (int i = 0; i < C; ++i) img_feat[(int64_t)(9 + i) * vol + idx] = var[i];
   }
 }
-
 
 // Backward wrt the feature maps (the images, projections and depths are data).  var_c = sq inv - (sum inv)^2 with
 // sum = f_ref + sum_v g_v, sq = f_ref^2 + sum_v g_v^2  =>  d var / d x = 2 inv (x - sum inv) for x in {f_ref, g_v}; g_v is the
@@ -142,9 +173,11 @@ __device__ __forceinline__ void scatter4(float* __restrict__ base, const Tap& t,
 }
 
 template <int NSRC>
-__global__ void __launch_bounds__(256) cost_volume_bwd_kernel(const float* __restrict__ feats_cl, Sweep sw, const float* __restrict__ depth,
-                                                              int C, int H, int W, int D, int pad, const float* __restrict__ g_var,
-                                                              float* __restrict__ g_feats_cl) {
+__global__ void __launch_bounds__(256) cost_volume_bwd_kernel(const float* __restrict__ feats_cl, const float* __restrict__ proj,
+                                                              const float* __restrict__ depth, int C, int H, int W, int D, int pad,
+                                                              const float* __restrict__ g_var, float* __restrict__ g_feats_cl) {
+  __shared__ float s_proj[kMaxSrc * 12];
+  load_proj(proj, NSRC, s_proj);
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
   const int64_t plane = (int64_t)Hp * Wp, vol = plane * D;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -160,13 +193,7 @@ __global__ void __launch_bounds__(256) cost_volume_bwd_kernel(const float* __res
   float cnt = 1.f;
 #pragma unroll
   for (int v = 0; v < NSRC; ++v) {
-    float s[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-      s[j] = __fadd_rn(dot3(gx0, gy0, 1.f, sw.r[v][3 * j], sw.r[v][3 * j + 1], sw.r[v][3 * j + 2]), __fdiv_rn(sw.t[v][j], dep));
-    const float u = __fdiv_rn(s[0], s[2]), w = __fdiv_rn(s[1], s[2]);
-    const float gx = __fsub_rn(__fdiv_rn(u, (float)(W - 1) / 2.f), 1.f), gy = __fsub_rn(__fdiv_rn(w, (float)(H - 1) / 2.f), 1.f);
-    make_tap(gx, gy, H, W, tap[v]);
+    sweep_tap(s_proj + 12 * v, gx0, gy0, dep, H, W, tap[v]);
     cnt += tap[v].mask;
   }
   const float inv = __fdiv_rn(1.0f, cnt);
@@ -197,63 +224,50 @@ __global__ void __launch_bounds__(256) cost_volume_bwd_kernel(const float* __res
   }
 }
 
-static void fill_sweep(Sweep& sw, const float* proj_host, int nsrc) {
-  for (int v = 0; v < nsrc; ++v) {
-    for (int j = 0; j < 3; ++j) {
-      for (int k = 0; k < 3; ++k) sw.r[v][3 * j + k] = proj_host[12 * v + 4 * j + k];
-      sw.t[v][j] = proj_host[12 * v + 4 * j + 3];
-    }
-  }
-}
-
 }  // namespace
 }  // namespace zest
 
 using namespace zest;
 
-extern "C" int zest_cost_volume_fwd(const float* feats_cl, const float* imgs_cl, const float* proj_host, const float* depth, int V, int C,
-                                    int H, int W, int D, int pad, float* img_feat, float* in_masks, void* stream) {
-  ZEST_CHECK_ARG(feats_cl && imgs_cl && proj_host && depth && img_feat && in_masks, "zest_cost_volume_fwd: null argument");
-  ZEST_CHECK_ARG(V >= 2 && V - 1 <= kMaxSrc && C > 0 && (C % 4) == 0 && H > 1 && W > 1 && D > 0 && pad >= 0,
+extern "C" int zest_cost_volume_fwd(const float* feats_cl, const float* imgs_cl, const float* proj, const float* depth, int V, int C,
+                                    int H, int W, int D, int pad, float* img_feat, float* in_masks, int channels_last, int cpad,
+                                    void* stream) {
+  ZEST_CHECK_ARG(feats_cl && imgs_cl && proj && depth && img_feat, "zest_cost_volume_fwd: null argument");
+  ZEST_CHECK_ARG(V >= 2 && V - 1 <= kMaxSrc && C > 0 && (C % 4) == 0 && C <= 32 && H > 1 && W > 1 && D > 0 && pad >= 0,
                  "zest_cost_volume_fwd: unsupported shape (V=%d C=%d H=%d W=%d D=%d pad=%d)", V, C, H, W, D, pad);
-  Sweep sw;
-  for (int v = 0; v < V - 1; ++v) {
-    for (int j = 0; j < 3; ++j) {
-      for (int k = 0; k < 3; ++k) sw.r[v][3 * j + k] = proj_host[12 * v + 4 * j + k];
-      sw.t[v][j] = proj_host[12 * v + 4 * j + 3];
-    }
-  }
+  ZEST_CHECK_ARG(!channels_last || (cpad >= 9 + C && (cpad % 4) == 0 && cpad <= 12 + C), "zest_cost_volume_fwd: cpad must be a multiple of 4 in [9 + C, 12 + C]");
   const int64_t vol = (int64_t)D * (H + 2 * pad) * (W + 2 * pad);
   const unsigned grid = (unsigned)((vol + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
-  switch (V - 1) {
-    case 1: cost_volume_kernel<1><<<grid, 256, 0, st>>>(feats_cl, imgs_cl, sw, depth, C, H, W, D, pad, img_feat, in_masks); break;
-    case 2: cost_volume_kernel<2><<<grid, 256, 0, st>>>(feats_cl, imgs_cl, sw, depth, C, H, W, D, pad, img_feat, in_masks); break;
-    case 3: cost_volume_kernel<3><<<grid, 256, 0, st>>>(feats_cl, imgs_cl, sw, depth, C, H, W, D, pad, img_feat, in_masks); break;
-    case 4: cost_volume_kernel<4><<<grid, 256, 0, st>>>(feats_cl, imgs_cl, sw, depth, C, H, W, D, pad, img_feat, in_masks); break;
+#define ZEST_CV(CQ)                                                                                                                  \
+  case CQ:                                                                                                                           \
+    if (channels_last) cost_volume_kernel<CQ, true><<<grid, 256, 0, st>>>(feats_cl, imgs_cl, proj, depth, V - 1, H, W, D, pad, cpad, img_feat, in_masks); \
+    else cost_volume_kernel<CQ, false><<<grid, 256, 0, st>>>(feats_cl, imgs_cl, proj, depth, V - 1, H, W, D, pad, cpad, img_feat, in_masks);              \
+    break;
+  switch (C / 4) {
+    ZEST_CV(1) ZEST_CV(2) ZEST_CV(4) ZEST_CV(8)
     default:
-      set_error("zest_cost_volume_fwd: %d source views not instantiated (1..4)", V - 1);
+      set_error("zest_cost_volume_fwd: %d feature channels not instantiated (4, 8, 16, 32)", C);
       return ZEST_E_ARG;
   }
+#undef ZEST_CV
   ZEST_LAUNCH_CHECK();
   return ZEST_OK;
 }
 
-extern "C" int zest_cost_volume_bwd(const float* feats_cl, const float* proj_host, const float* depth, int V, int C, int H, int W, int D,
+extern "C" int zest_cost_volume_bwd(const float* feats_cl, const float* proj, const float* depth, int V, int C, int H, int W, int D,
                                     int pad, const float* g_var, float* g_feats_cl, void* stream) {
-  ZEST_CHECK_ARG(feats_cl && proj_host && depth && g_var && g_feats_cl, "zest_cost_volume_bwd: null argument");
+  ZEST_CHECK_ARG(feats_cl && proj && depth && g_var && g_feats_cl, "zest_cost_volume_bwd: null argument");
   ZEST_CHECK_ARG(V >= 2 && V - 1 <= 4 && C > 0 && (C % 4) == 0 && H > 1 && W > 1 && D > 0 && pad >= 0,
-                 "zest_cost_volume_bwd: unsupported shape (V=%d C=%d H=%d W=%d D=%d pad=%d)", V, C, H, W, D, pad);
-  Sweep sw;
-  fill_sweep(sw, proj_host, V - 1);
+                 "zest_cost_volume_bwd: unsupported shape (V=%d C=%d H=%d W=%d D=%d pad=%d; at most 4 source views)", V, C, H, W, D, pad);
   const int64_t vol = (int64_t)D * (H + 2 * pad) * (W + 2 * pad);
   const unsigned grid = (unsigned)((vol + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   switch (V - 1) {
-    case 1: cost_volume_bwd_kernel<1><<<grid, 256, 0, st>>>(feats_cl, sw, depth, C, H, W, D, pad, g_var, g_feats_cl); break;
-    case 2: cost_volume_bwd_kernel<2><<<grid, 256, 0, st>>>(feats_cl, sw, depth, C, H, W, D, pad, g_var, g_feats_cl); break;
-    case 3: cost_volume_bwd_kernel<3><<<grid, 256, 0, st>>>(feats_cl, sw, depth, C, H, W, D, pad, g_var, g_feats_cl); break;
-    default: cost_volume_bwd_kernel<4><<<grid, 256, 0, st>>>(feats_cl, sw, depth, C, H, W, D, pad, g_var, g_feats_cl); break;
+    case 1: cost_volume_bwd_kernel<1><<<grid, 256, 0, st>>>(feats_cl, proj, depth, C, H, W, D, pad, g_var, g_feats_cl); break;
+    case 2: cost_volume_bwd_kernel<2><<<grid, 256, 0, st>>>(feats_cl, proj, depth, C, H, W, D, pad, g_var, g_feats_cl); break;
+    case 3: cost_volume_bwd_kernel<3><<<grid, 256, 0, st>>>(feats_cl, proj, depth, C, H, W, D, pad, g_var, g_feats_cl); break;
+    default: cost_volume_bwd_kernel<4><<<grid, 256, 0, st>>>(feats_cl, proj, depth, C, H, W, D, pad, g_var, g_feats_cl); break;
   }
   ZEST_LAUNCH_CHECK();
   return ZEST_OK;

@@ -165,7 +165,7 @@ extern "C" zest_net* zest_net_create(int kind, int in_pts, int in_feat, int in_v
   n->width = width; n->depth = depth; n->skip = skip;
   n->out_ch = kind == 0 ? 4 : (kind == 1 ? 5 : 12);
   n->n_small = kind == 0 ? 1 : (kind == 1 ? 2 : 9);
-  n->packed = false; n->f32 = nullptr; n->tc_blob = nullptr; n->tc_bias = nullptr; n->tc_plan_host = nullptr; n->tc_bytes = 0; n->tc_desc_dev = nullptr; n->tc_dirty = true;
+  n->packed = false; n->f32 = nullptr; n->tc_blob = nullptr; n->tc_bias = nullptr; n->tc_plan_host = nullptr; n->tc_bytes = 0; n->tc_desc_dev = nullptr; n->tc_dirty = true; n->tc_counters = nullptr; n->tc_counter_next = 0;
   // blob layout; the stacked small heads keep alpha first so column 0 of SH is sigma
   int64_t o = 0;
   int pi = 0;

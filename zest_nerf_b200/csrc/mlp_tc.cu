@@ -106,6 +106,7 @@ struct TcParams {
   int P, Ppad, F, Fpad;
   int kind, out_ch, overlap;
   int64_t M; int64_t n_tiles;
+  int* tile_counter;   // dynamic tile scheduler: next unclaimed tile (zeroed before the launch); nullptr = static round-robin
   float* raw;
   unsigned long long* tl;  // debug timeline buffer (ZEST_TC_TIMELINE builds only)
 };
@@ -331,7 +332,8 @@ template <int C, bool GATE32, int kLoadWarps, int CL>  // C = 3 (static: xyz) or
                                                        // CL = 2: CTA pairs (clusters) share every weight stage via TMA multicast
 __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_bars[2 * kStages + 10];
+  __shared__ __align__(8) uint64_t s_bars[2 * kStages + 14];
+  __shared__ int s_tile[4];
   __shared__ float s_cams[kMaxViews * 24];
   __shared__ uint32_t s_tmem;
 
@@ -350,6 +352,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
   b.acc_free = b.acc_full + 16; b.a_ready = b.acc_free + 16;
   // loader handshake: inputs of tile #it staged (4 loader warps) / feats operand free (GATE retired) / PE operand free (L5 retired)
   const uint32_t in_ready = b.a_ready + 24, feats_free = in_ready + 8, pe_free = in_ready + 16;
+  const uint32_t tile_bar = in_ready + 24;   // 4 barriers: tile id #it of this CTA published in s_tile[it & 3]
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { ptx::mbar_init(b.full + 8 * s, 1); ptx::mbar_init(b.empty + 8 * s, CL); }
@@ -360,6 +363,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
     }
     ptx::mbar_init(b.a_ready + 16, kEpiWarps);
     ptx::mbar_init(in_ready, kLoadWarps); ptx::mbar_init(feats_free, 1); ptx::mbar_init(pe_free, 1);
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(tile_bar + 8 * i, 1);
     ptx::fence_mbar_init();
   }
   if (!kBiasInMma) for (int i = tid; i < kBiasOps * 256; i += kThreads) ptx::st_smem_u32(bias_s0 + i * 4, __float_as_uint(__ldg(p.bias + i)));
@@ -383,6 +387,30 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
   const int64_t first_cta = (CL == 2) ? (blockIdx.x & ~1u) : blockIdx.x;
   const int64_t my_tiles = (p.n_tiles > first_cta) ? (p.n_tiles - first_cta + gridDim.x - 1) / gridDim.x : 0;
   const uint32_t cta_rank = (CL == 2) ? ptx::cluster_ctarank() : 0u;
+  // Tile schedule.  Dynamic (default): the first loader warp claims the CTA's next tile from a global counter and
+  // publishes it in s_tile[it & 3] behind tile_bar[it & 3]; every other role picks it up there.  A CTA that starts late
+  // or shares its SM with another stream's kernel (a collective waiting for a peer, a copy kernel) simply claims fewer
+  // tiles - with the static round-robin one delayed CTA delayed the whole launch by its full tile list.  The leader is
+  // never more than two tiles ahead of the slowest role (feats_free), so four slots cannot wrap.
+  const bool dyn = (CL == 1) && p.tile_counter != nullptr;
+  auto tile_static = [&](int64_t it) -> int64_t { return it < my_tiles ? (int64_t)blockIdx.x + it * (int64_t)gridDim.x : -1; };
+  auto tile_lead = [&](int64_t it) -> int64_t {
+    if (!dyn) return tile_static(it);
+    int t = 0;
+    if (lane == 0) {
+      t = atomicAdd(p.tile_counter, 1);
+      s_tile[it & 3] = t;
+      ptx::mbar_arrive(tile_bar + 8 * (uint32_t)(it & 3));   // release: orders the store above
+    }
+    t = __shfl_sync(0xffffffffu, t, 0);
+    return t < p.n_tiles ? (int64_t)t : -1;
+  };
+  auto tile_follow = [&](int64_t it) -> int64_t {
+    if (!dyn) return tile_static(it);
+    wait_bar(tile_bar + 8 * (uint32_t)(it & 3), (uint32_t)((it >> 2) & 1), 500);
+    const int t = ((volatile int*)s_tile)[it & 3];
+    return t < p.n_tiles ? (int64_t)t : -1;
+  };
   if (CL == 2) ptx::cluster_sync();   // the peer's barriers are initialised before anything is multicast into this CTA
 
   if (warp == kEpiWarps) {
@@ -390,7 +418,8 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
     // The whole warp runs the loop convergently (addresses stay in uniform registers); one elected
     // lane arms the barrier and issues the bulk copy.  Stage s always lands in slot s % 4.
     uint32_t phase = 0;
-    for (int64_t it = 0; it < my_tiles; ++it) {
+    for (int64_t it = 0;; ++it) {
+      if (tile_follow(it) < 0) break;
       for (int s0 = 0; s0 < p.n_stages; s0 += kStages) {
 #pragma unroll
         for (int slot = 0; slot < kStages; ++slot) {
@@ -429,10 +458,13 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
     const uint32_t acc0 = tmem + ACC_COL_OF(0), acc1 = tmem + ACC_COL_OF(1), act = tmem + ACT_COL;
     const bool ov = p.overlap != 0;
     const int nk_f = p.Fpad / 16, nk_p = p.Ppad / 16;
-    for (int64_t it = 0; it < my_tiles; ++it) {
+    for (int64_t it = 0;; ++it) {
+      if (!dyn && it >= my_tiles) break;
       c.n_issued = 0;
       // ---- revolution 0: GATE (feats, SS) | L0 (PE, SS) ----
       wait_bar(in_ready, (uint32_t)(it & 1), 210);   // the loader warps have staged this tile's operands
+      // dynamic schedule: the loaders also arrive on in_ready for the end-of-work sentinel, published before that arrival
+      if (dyn && ((volatile int*)s_tile)[it & 3] >= p.n_tiles) break;
       c.next_op(); c.wait(31u);
       mma_stage<128, false, 0>(c, feat_lo, nk_f, acc0, true, kBiasInMma, 0);
       mma_stage<128, false, 1>(c, feat_lo, nk_f, acc1, true, kBiasInMma, 1);
@@ -525,12 +557,20 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
     // feats_free / pe_free (tcgen05.commit behind their last readers); dirPE (read by VIEWS at the very end of a
     // tile) is double buffered by tile parity.
     const int row0 = (warp - (kEpiWarps + 2)) * 32 + lane;   // this thread stages rows row0 and row0 + 64
-    for (int64_t it = 0; it < my_tiles; ++it) {
+    const bool leader = warp == kEpiWarps + 2;
+    for (int64_t it = 0;; ++it) {
+      const int64_t tile = leader ? tile_lead(it) : tile_follow(it);
+      if (tile < 0 && !dyn) break;
       if (it > 0) wait_bar(feats_free, (uint32_t)((it - 1) & 1), 400);
+      if (tile < 0) {   // dynamic schedule, no tile left: wake the MMA warp (it reads the sentinel behind in_ready) and leave
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(in_ready);
+        break;
+      }
 #pragma unroll 1
       for (int h = 0; h < kRowsPerLoader; ++h) {
         const int row = row0 + 32 * kLoadWarps * h;
-        const int64_t m = (blockIdx.x + it * gridDim.x) * kTile + row;
+        const int64_t m = tile * kTile + row;
         const bool valid = m < p.M;
         // ---- gathered features: fused trilinear volume sample + per-view bilinear RGB + mask (gather_core.cuh),
         //      or pre-gathered feats / the feat block of x.  The feats operand is free once GATE(it-1) has retired. ----
@@ -589,7 +629,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
 #pragma unroll 1
       for (int h = 0; h < kRowsPerLoader; ++h) {
         const int row = row0 + 32 * kLoadWarps * h;
-        const int64_t m = (blockIdx.x + it * gridDim.x) * kTile + row;
+        const int64_t m = tile * kTile + row;
         const bool valid = m < p.M;
         // ---- direction PE (this tile parity's buffer: its last reader, VIEWS two tiles ago, retired long ago) ----
         {
@@ -613,7 +653,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
 #pragma unroll 1
       for (int h = 0; h < kRowsPerLoader; ++h) {
         const int row = row0 + 32 * kLoadWarps * h;
-        const int64_t m = (blockIdx.x + it * gridDim.x) * kTile + row;
+        const int64_t m = tile * kTile + row;
         const bool valid = m < p.M;
         // ---- point PE ----
         {
@@ -644,8 +684,10 @@ __global__ void __launch_bounds__(32 * (kEpiWarps + 2 + kLoadWarps), 1) mlp_tc_k
     uint32_t nfull[2] = {0, 0};
     int tl_n[2] = {0, 0}; (void)tl_n;
     const uint32_t tmem_lane = tmem + ((uint32_t)(q * 32) << 16);
-    for (int64_t it = 0; it < my_tiles; ++it) {
-      const int64_t m = (blockIdx.x + it * gridDim.x) * kTile + row;
+    for (int64_t it = 0;; ++it) {
+      const int64_t tile = tile_follow(it);
+      if (tile < 0) break;
+      const int64_t m = tile * kTile + row;
       const bool valid = m < p.M;
       // tile start: stands for "the previous tile's RGB epilogue is done" on all four epilogue -> MMA barriers
       ptx::tc_fence_before();
@@ -878,12 +920,14 @@ __global__ void __launch_bounds__(128, 1) tc_rate_kernel(int reps, int ts, int l
 
 // ------------------------------------------------------------------------------------------------
 static inline int up(int v, int m) { return (v + m - 1) / m * m; }
+constexpr int kTileCounters = 64;
 
 void tc_free(zest_net* net) {
   if (net->tc_blob) cudaFree(net->tc_blob);
   if (net->tc_bias) cudaFree(net->tc_bias);
   if (net->tc_desc_dev) cudaFree(net->tc_desc_dev);
-  net->tc_desc_dev = nullptr;
+  if (net->tc_counters) cudaFree(net->tc_counters);
+  net->tc_desc_dev = nullptr; net->tc_counters = nullptr;
   if (net->tc_plan_host) delete (TcPlanHost*)net->tc_plan_host;
   net->tc_blob = nullptr; net->tc_bias = nullptr; net->tc_plan_host = nullptr;
 }
@@ -949,6 +993,7 @@ int tc_pack(zest_net* net, cudaStream_t st) {
     ZEST_CUDA(cudaMalloc(&net->tc_blob, (size_t)blob_off));
     ZEST_CUDA(cudaMalloc(&net->tc_bias, (size_t)kBiasOps * 256 * sizeof(float)));
     ZEST_CUDA(cudaMalloc(&net->tc_desc_dev, packs.size() * sizeof(PackDesc)));
+    ZEST_CUDA(cudaMalloc(&net->tc_counters, kTileCounters * sizeof(int)));
     ZEST_CUDA(cudaMemcpy(net->tc_desc_dev, packs.data(), packs.size() * sizeof(PackDesc), cudaMemcpyHostToDevice));
     net->tc_bytes = blob_off;
     ph->n_packs = (int)packs.size();
@@ -992,6 +1037,16 @@ static int tc_launch(const zest_net* net, TcParams& p, cudaStream_t st) {
   p.kind = net->kind; p.out_ch = net->out_ch; p.overlap = ph->overlap;
   p.n_tiles = (p.M + kTile - 1) / kTile;
   if (p.M == 0) return ZEST_OK;
+  ZEST_CHECK_ARG(p.n_tiles < (1ll << 30), "zest_mlp_fwd_tc: too many rows for one launch");
+  // dynamic tile scheduler: one zeroed counter per launch out of a small ring (launches of one net that are in flight
+  // at the same time on different streams must not share a counter); ZEST_TC_STATIC=1 keeps the static round-robin
+  static const bool force_static = getenv("ZEST_TC_STATIC") && atoi(getenv("ZEST_TC_STATIC")) != 0;
+  p.tile_counter = nullptr;
+  if (!force_static && !ph->cluster2 && net->tc_counters) {
+    zest_net* mut = const_cast<zest_net*>(net);
+    p.tile_counter = net->tc_counters + (mut->tc_counter_next++ % kTileCounters);
+    ZEST_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(int), st));
+  }
   int grid = (int)(p.n_tiles < num_sms() ? p.n_tiles : num_sms());
   const bool wide = p.vol && p.V > 6;   // many source views: the in-kernel gather needs four loader warps
   // ZEST_TC_CLUSTER=2 (experiment, default off): CTA pairs share every weight stage through TMA multicast, halving the

@@ -30,6 +30,8 @@ struct zest_net {
   float* tc_bias;      // device: [11][256] fp32 biases of the 256-wide ops, read by the tensor-core kernel's epilogue
   void* tc_plan_host;  // host: layer plan (opaque to everything but mlp_tc.cu)
   void* tc_desc_dev;   // device: pack descriptors (uploaded once)
+  int* tc_counters;    // device: ring of tile-scheduler counters (one per launch in flight)
+  unsigned tc_counter_next;
   bool tc_dirty;       // f32 changed since the bf16 image was built: rebuilt lazily by the next tensor-core launch
 };
 

@@ -6,10 +6,14 @@ Per time-frame the encoding volumes, source / neighbour views and camera tables 
 (a "frame slot", already in the channels-last layouts the kernels read).  The rank that produced them packs straight into
 its slot and the other ranks receive the packed bytes - nobody re-lays 82.5 MiB volumes per rank - over one of two
 transports:
-  * "nccl": one `torch.distributed.broadcast` of the flat buffer (NCCL over NVLink), or
+  * "nccl" (default): one `torch.distributed.broadcast` of the flat buffer (NCCL over NVLink / NVSwitch).  Its kernel
+            shares the SMs with the render kernel of the current frame, which is why that kernel claims its tiles
+            dynamically (csrc/mlp_tc.cu): a CTA that starts late or loses its SM for a while just renders fewer tiles.
   * "ipc":  every rank maps the source rank's slot through CUDA IPC once and pulls it with a peer-to-peer
-            `cudaMemcpyAsync` (copy engines over NVLink / NVSwitch: no SM is taken from the render kernels); two
-            one-element NCCL all-reduces on the side stream order the pull against the source's pack kernels.
+            `cudaMemcpyAsync` (copy engines: no SM taken); two one-element NCCL all-reduces on the side stream order the
+            pull against the source's pack kernels.  Stand-alone it is the faster transport (0.37 vs 0.6 ms for 190 MB
+            between two B200s), pipelined under a render it measured slower (the receiving rank's render is enqueued
+            late), so it is opt-in (`transport="ipc"` / ZEST_FRAME_TRANSPORT=ipc).
 Slots are double-buffered and filled on a side stream, so frame k+1 is distributed under the kernels of frame k
 (`prefetch_frame` / `swap_frame`; `set_frame` = both, back to back).  Per target pose every rank renders a contiguous
 slab of the row-major pixel grid; `gather_maps` collects the per-ray maps with ONE all-gather of a packed [rays, 13]
@@ -98,7 +102,7 @@ class FrameRenderer:
         self.frame = None
         # bf16 inference: gather + PE + MLP in one launch per net (ZEST_FUSED_GATHER=0: separate gather kernel)
         self.fused = os.environ.get("ZEST_FUSED_GATHER", "1") != "0"
-        self.transport = (transport or os.environ.get("ZEST_FRAME_TRANSPORT", "ipc")).lower()
+        self.transport = (transport or os.environ.get("ZEST_FRAME_TRANSPORT", "nccl")).lower()
         if self.transport not in ("ipc", "nccl"):
             raise ValueError("transport must be 'ipc' or 'nccl'")
         self.cuda = self.device.type == "cuda"
@@ -109,6 +113,13 @@ class FrameRenderer:
         self._flag = None
         self._gather_buf = {}
         self.transport_used = None
+        self.trace = [] if os.environ.get("ZEST_FRAME_TRACE") else None     # (name, timing event) pairs, developer timeline
+
+    def _mark(self, name, stream=None):
+        if self.trace is not None and self.cuda:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream if stream is not None else torch.cuda.current_stream(self.device))
+            self.trace.append((name, e))
 
     # ------------------------------------------------------------------ per time-frame state
     def _ensure_slots(self, layout):
@@ -170,8 +181,10 @@ class FrameRenderer:
             self.side.wait_event(entry)
             if slot.released is not None:
                 self.side.wait_event(slot.released)          # this rank's last render from the slot is finished
+            self._mark("side:start")
             if multi and self.transport == "ipc":
                 self._tick()                                  # every rank's earlier pull from this slot is finished
+            self._mark("side:tickA")
             if is_src:
                 lib = _lib.load()
                 t = slot.t
@@ -190,8 +203,10 @@ class FrameRenderer:
                     _lib.check(lib.zest_pack_images(ops._ptr(f32(nb_imgs, "nb_imgs")), ops._ptr(t["nb"]), NB, layout.H, layout.W,
                                                     ops._stream()), "zest_pack_images")
                     t["cams_d"].copy_(ops.cam_table(nb_cam_mat, NB))
+            self._mark("side:packed")
             if multi:
                 self._distribute(slot, nxt, src)
+            self._mark("side:distributed")
             slot.ready = torch.cuda.Event()
             slot.ready.record(self.side)
         self._pending = nxt
@@ -201,6 +216,7 @@ class FrameRenderer:
         """Called with the side stream current: move the packed bytes of `slot` from `src` to every rank."""
         if self.transport == "ipc" and self._handles is not None:
             self._tick()                                       # src's pack kernels are finished (stream-ordered on every rank)
+            self._mark("side:tickB")
             if self.rank != src:
                 slot.flat.copy_(self._peer_slots(src)[idx], non_blocking=True)    # peer-to-peer pull: copy engines
             self.transport_used = "ipc"
@@ -337,10 +353,12 @@ class FrameRenderer:
             parts = [torch.empty_like(mine) for _ in range(self.world)]
             torch.distributed.all_gather(parts, mine, group=self.group)
             full.copy_(torch.cat(parts, 0))
+        # the maps are returned as column VIEWS of the gathered [rays, C] tensor (no copy kernels): `.contiguous()` them if a
+        # consumer needs dense storage, or read `_packed` (one device -> host copy moves every map of the frame)
         out, c = {}, 0
         for k, w in zip(keys, widths):
             col = full[:n_rays, c:c + w]
-            out[k] = col.reshape(1, n_rays, 3).contiguous() if w == 3 else col.reshape(1, n_rays).contiguous()
+            out[k] = col.unsqueeze(0) if w == 3 else col[:, 0].unsqueeze(0)
             c += w
         out["_packed"] = full[:n_rays]
         return out
