@@ -463,6 +463,39 @@ def cost_volume_stage(dev, pk, reps=5):
             "note": "algorithmic bytes = the volume and masks written once (44 x 4 B per voxel); the feature maps (3.5 MB) stay in cache"}
 
 
+def mvsnet_stage(dev, pk, reps=3):
+    """"Next" row f3 (second half): the whole encoding-volume builder at NSFF shape - FeatureNet on 3 views of 288 x 512,
+    plane-sweep cost volume (channels-last, 128-bit stores), CostRegNet 3-D U-Net with batch-statistics InPlaceABN - through
+    `mvs.MVSNet.forward`.  The 3-D convolutions run in exact fp32 on the CUDA cores (31 GMAC, 77 % of them in CostRegNet.conv0),
+    so the stage is FMA-issue bound: reported against the fp32 FMA peak of the part at the clock it ran at."""
+    import torch
+    from zest_nerf_b200 import mvs
+    g = torch.Generator(device=dev).manual_seed(3)
+    V, H, W, pad = 3, 288, 512, 24
+    net = mvs.MVSNet().to(dev)
+    imgs = torch.randn((1, V, 3, H, W), device=dev, generator=g)
+    proj = torch.eye(4, device=dev)[:3][None, None].repeat(1, V, 1, 1)
+    proj[0, 1, 0, 3], proj[0, 2, 0, 3] = 8.0, -8.0
+    nf = torch.tensor([2.0, 6.0], device=dev)
+    net(imgs, proj, nf, pad=pad)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(reps):
+        vol, _, _ = net(imgs, proj, nf, pad=pad)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    vox = 128 * 120 * 176
+    macs = vox * 27 * (41 * 8 + 8 * 16 / 8 + 16 * 16 / 8 + 16 * 32 / 64 + 32 * 32 / 64 + 32 * 64 / 512 + 64 * 64 / 512) \
+        + vox * (64 * 32 * 27 / 8 / 64 + 32 * 16 * 27 / 8 / 8 + 16 * 8 * 27 / 8)
+    fmacs = V * 288 * 512 * (27 * 8 + 72 * 8) + V * 144 * 256 * (200 * 16 + 2 * 144 * 16) + V * 72 * 128 * (400 * 32 + 2 * 288 * 32 + 32 * 32)
+    peak = 148 * 128 * 2 * 1.9e9 / 1e12
+    tf = 2.0 * (macs + fmacs) / (ms * 1e-3) / 1e12
+    return {"api": "zest_nerf_b200.mvs.MVSNet.forward (FeatureNet + cost volume + CostRegNet, batch-statistics InPlaceABN)", "ms": ms,
+            "gmac": (macs + fmacs) / 1e9, "achieved_fp32_tflops": tf, "fp32_fma_peak_tflops_nominal": peak, "frac_of_fp32_fma_peak": tf / peak,
+            "volume_shape": list(vol.shape), "hbm_floor_ms": (vox * 44 * 4 * 2 + vox * 8 * 4 * 6) / (pk["hbm_gbs"] * 1e6),
+            "note": "exact-fp32 CUDA-core convolutions (the reference's CPU arithmetic; cuDNN would use TF32): bound by FMA issue, not HBM"}
+
+
 FT_ENGINE_NAMES = {0: "fp32 CUDA cores (sgemm)", 1: "tcgen05 3 x bf16, one accumulator", 2: "tcgen05 3 x tf32, split accumulators (default)"}
 
 
@@ -997,10 +1030,14 @@ def main():
     if rank == 0 and world == 1 and c["dynamic"] and not args.no_fine_tune:
         ft = fine_tune_report(fine_tune_stage(sc, dev, lib, H, W, steps=3, warmup=2, engines=(2, 1)), V, pk)
 
-    f4 = f3 = None
+    f4 = f3 = f3b = None
     if rank == 0 and world == 1 and not args.no_fine_tune:
         f4 = sf_loss_stage(dev, pk, H, W)
         f3 = cost_volume_stage(dev, pk)
+        try:
+            f3b = mvsnet_stage(dev, pk)
+        except Exception as e:
+            f3b = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -1036,7 +1073,7 @@ def main():
                 "steps_ms": [round(x, 3) for x in ms], "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 3), "clocks": clocks, "roofline": roofline, "e2e": e2e,
                 "cpu_baseline": cpu, "parity": parity, "torch_gpu_baseline": tgpu, "sharded_frame_equals_single_gpu": sharded_ok,
                 "pose_parallel_weak": pose_parallel, "cfg3_strong": cfg3_strong,
-                "gather_stage": gstage, "fine_tune": ft, "next_rows": {"f1_ray_builder": f1, "f3_cost_volume": f3, "f4_sf_losses": f4}}
+                "gather_stage": gstage, "fine_tune": ft, "next_rows": {"f1_ray_builder": f1, "f3_cost_volume": f3, "f3_mvsnet": f3b, "f4_sf_losses": f4}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

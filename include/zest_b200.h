@@ -26,6 +26,9 @@
  *   zest_project_ndc_fwd / _bwd           utils.py:516-539 projection_from_ndc (+ :507-514 NDC2Euclidean)
  *   zest_cost_volume_fwd / _bwd           networks.py:1077-1140 MVSNet.build_volume_cost + utils.py:49-99 homo_warp
  *                                         ("next" row f3, first half)
+ *   zest_conv_cl_fwd / zest_convt3_cl_fwd / zest_bn_act_cl / zest_resize_bilinear_cl / zest_conv_pack_weights
+ *                                         networks.py:935-1059 FeatureNet + CostRegNet with InPlaceABN ("next" row f3,
+ *                                         second half), :1142-1238 MVSNet.forward
  *
  * Conventions
  *   - Every pointer is a DEVICE pointer into memory owned by the caller (PyTorch); the library
@@ -190,17 +193,46 @@ int zest_project_ndc_bwd(const float* w2c, const float* weights, const float* ra
 
 /* ---- plane-sweep cost volume ("next" row f3, first half) ---------------------------------------------
  * networks.py:1077-1140 MVSNet.build_volume_cost + utils.py:49-99 homo_warp in one pass.
- * feats_cl [V, C/4, H, W, 4] feature maps as planes of channel quads (view 0 = reference, C % 4 == 0), imgs_cl [V, H, W, 4] the images at
- * feature resolution (r, g, b, 0), proj_host: HOST pointer, (V - 1) x 12 floats = rows of the 3x4 "src_proj @ ref_proj_inv"
- * of every source view, depth [D] plane depths (device).  Outputs (NCDHW, Hp = H + 2 pad, Wp = W + 2 pad):
- * img_feat [3 V + C, D, Hp, Wp] = reference image (zero outside the unpadded window), warped source images, variance of the
- * features over the views; in_masks [V, D, Hp, Wp] = 1 for the reference, -1 < grid < 1 for the source views. */
-int zest_cost_volume_fwd(const float* feats_cl, const float* imgs_cl, const float* proj_host, const float* depth,
-                         int V, int C, int H, int W, int D, int pad, float* img_feat, float* in_masks, void* stream);
-/* Backward wrt the feature maps: g_var = gradient of the C variance channels ([C, D, Hp, Wp], i.e. img_feat + 3 V channels),
- * g_feats_cl [V, C/4, H, W, 4] is ACCUMULATED into (zero it first).  Images, projections and depths are data. */
-int zest_cost_volume_bwd(const float* feats_cl, const float* proj_host, const float* depth, int V, int C, int H, int W,
+ * feats_cl [V, C/4, H, W, 4] feature maps as planes of channel quads (view 0 = reference, C in {4, 8, 16, 32}), imgs_cl [V, H, W, 4]
+ * the images at feature resolution (r, g, b, 0), proj [(V - 1), 12] (DEVICE) = rows of the 3x4 "src_proj @ ref_proj_inv" of
+ * every source view (V - 1 <= 9), depth [D] plane depths.  Hp = H + 2 pad, Wp = W + 2 pad.  The volume has 9 + C channels
+ * whatever V is, like the reference's (`torch.empty((B, 9 + 32, ...))`, networks.py:1101; the warped images of source views
+ * beyond the second fall on channels the variance overwrites, :1138): reference image (zero outside the unpadded window),
+ * warped images of source views 1 and 2, variance of the features over all V views.
+ *   channels_last == 0: img_feat [9 + C, D, Hp, Wp] (the reference's layout), in_masks [V, D, Hp, Wp] (= 1 for the reference,
+ *                       -1 < grid < 1 for the source views; may be NULL)
+ *   channels_last != 0: img_feat [D, Hp, Wp, cpad] with 9 + C <= cpad <= 12 + C, cpad % 4 == 0, pad channels zero - the input
+ *                       layout of zest_conv_cl_fwd; in_masks is not written */
+int zest_cost_volume_fwd(const float* feats_cl, const float* imgs_cl, const float* proj, const float* depth,
+                         int V, int C, int H, int W, int D, int pad, float* img_feat, float* in_masks,
+                         int channels_last, int cpad, void* stream);
+/* Backward wrt the feature maps: g_var = gradient of the C variance channels ([C, D, Hp, Wp], i.e. img_feat + 9 channels),
+ * g_feats_cl [V, C/4, H, W, 4] is ACCUMULATED into (zero it first).  Images, projections and depths are data.  V - 1 <= 4. */
+int zest_cost_volume_bwd(const float* feats_cl, const float* proj, const float* depth, int V, int C, int H, int W,
                          int D, int pad, const float* g_var, float* g_feats_cl, void* stream);
+
+/* ---- encoding-volume CNNs ("next" row f3, second half): networks.py:935-1059 FeatureNet / CostRegNet ------------
+ * Channels-last fp32 activations [N (images) or D (planes), H, W, C].  Weights are repacked once per parameter version:
+ * w = nn.Conv2d/3d weight [cout, cin, kd, kh, kw] (transposed == 0) or nn.ConvTranspose3d weight [cin, cout, 3, 3, 3]
+ * (transposed != 0) -> packed [cout / 8][kd kh kw][cin_pad][8], cin_pad % 4 == 0 (extra input channels get zero weights). */
+int zest_conv_pack_weights(const float* w, int cout, int cin, int kd, int kh, int kw, int transposed, int cin_pad,
+                           float* packed, void* stream);
+/* y [No, Ho, Wo, cout] = conv(x [N, H, W, cin]) (+ bias), "same" padding k / 2, stride 1 or 2 (kd == 1: 2-D convolution of
+ * N images; kd == 3: 3-D over N planes).  Instantiated: 3x3x3 s1/s2, 1x3x3 s1, 1x5x5 s2, 1x1x1 s1.  stats (optional): double
+ * [2 cout], zeroed and filled with per-channel sum and sum of squares of y (the batch statistics InPlaceABN normalises with). */
+int zest_conv_cl_fwd(const float* x, int N, int H, int W, int cin, const float* wpacked, const float* bias, int cout,
+                     int kd, int kh, int kw, int stride, float* y, double* stats, void* stream);
+/* nn.ConvTranspose3d(cin, cout, 3, padding=1, output_padding=1, stride=2, bias=False): y [2 D, 2 H, 2 W, cout]. */
+int zest_convt3_cl_fwd(const float* x, int D, int H, int W, int cin, const float* wpacked, int cout, float* y,
+                       double* stats, void* stream);
+/* InPlaceABN forward over n rows of C channels: y = leaky_relu(bn(x), slope) (+ skip, an already activated tensor of the same
+ * shape: the U-Net additions networks.py:1049-1055).  training != 0: batch statistics from `stats` (zest_conv_cl_fwd), running
+ * statistics updated with `momentum` (unbiased variance) when given; training == 0: running statistics.  y may alias x. */
+int zest_bn_act_cl(const float* x, int64_t n, int C, const double* stats, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, float eps, float momentum, float slope, int training,
+                   const float* skip, float* y, void* stream);
+/* F.interpolate(mode="bilinear", align_corners=False) of packed images [V, H, W, 4] -> [V, h, w, 4] (networks.py:1102). */
+int zest_resize_bilinear_cl(const float* x, int V, int H, int W, int h, int w, float* y, void* stream);
 
 /* ---- alpha compositing (warp per ray) ---------------------------------------------------- */
 /* raw [R*S, ld_raw] (rgb_raw 3, sigma_raw 1, ...), z [R,S], cos_angle [R], noise [R,S] or NULL

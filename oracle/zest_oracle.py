@@ -366,13 +366,15 @@ def plane_sweep_grid(proj, depth_values, H, W, pad):
 def cost_volume(imgs, feats, proj_mats, depth_values, pad=0):
     """`networks.py:1077-1140` MVSNet.build_volume_cost (eval mode) for B = 1: reference-view image and zero-padded features
     broadcast over the depth planes, every source view warped by `plane_sweep_grid` + bilinear sampling (zeros padding,
-    align_corners=True), variance over the views with the in-frustum count.  The border of the first 3 channels (uninitialised
-    memory in the reference, `:1101-1103`) is zero here."""
+    align_corners=True), variance over the views with the in-frustum count.  The volume has 9 + C channels whatever V is
+    (`torch.empty((B, 9 + 32, ...))`, `:1101`): the warped images of source views beyond the second fall on channels that the
+    variance (`img_feat[:, -32:]`, `:1138`) overwrites.  The border of the first 3 channels (uninitialised memory in the
+    reference, `:1101-1103`; channels 6:9 too when V = 2) is zero here."""
     _, V, C, H, W = feats.shape
     D = depth_values.shape[1]
     Hp, Wp = H + 2 * pad, W + 2 * pad
     small = F.interpolate(imgs[0], (H, W), mode="bilinear", align_corners=False)             # [V, 3, H, W]
-    out = torch.zeros((1, 3 * V + C, D, Hp, Wp))
+    out = torch.zeros((1, 9 + C, D, Hp, Wp))
     out[0, :3, :, pad:H + pad, pad:W + pad] = small[0].unsqueeze(1)
     ref = F.pad(feats[0, 0], (pad, pad, pad, pad)).unsqueeze(1).expand(C, D, Hp, Wp)
     total, total_sq = ref.clone(), ref ** 2
@@ -381,11 +383,56 @@ def cost_volume(imgs, feats, proj_mats, depth_values, pad=0):
         grid = plane_sweep_grid(proj_mats[0, v], depth_values[0], H, W, pad)
         g = grid.view(1, D, Hp * Wp, 2)
         warped = F.grid_sample(feats[:, v], g, mode="bilinear", padding_mode="zeros", align_corners=True).view(C, D, Hp, Wp)
-        out[0, 3 * v:3 * v + 3] = F.grid_sample(small[v:v + 1], g, mode="bilinear", padding_mode="zeros",
-                                                align_corners=True).view(3, D, Hp, Wp)
+        if v <= 2:
+            out[0, 3 * v:3 * v + 3] = F.grid_sample(small[v:v + 1], g, mode="bilinear", padding_mode="zeros",
+                                                    align_corners=True).view(3, D, Hp, Wp)
         masks[0, v] = ((grid > -1.0) & (grid < 1.0)).all(-1).float()
         total = total + warped
         total_sq = total_sq + warped ** 2
     count = 1.0 / masks.sum(1)
-    out[0, 3 * V:] = total_sq * count - (total * count) ** 2
+    out[0, 9:] = total_sq * count - (total * count) ** 2
     return out, masks
+
+
+# --------------------------------------------------------------------------- "next" row f3 (second half): the encoding CNNs
+def _abn(x, sd, p, training, eps=1e-5, momentum=0.1, slope=0.01):
+    """InPlaceABN = batch norm + leaky ReLU(0.01) (`networks.py:942,955`); training: batch statistics (the reference keeps
+    the encoders in train() mode even for validation, `networks.py:626`)."""
+    y = F.batch_norm(x, sd[p + "running_mean"].clone(), sd[p + "running_var"].clone(), sd.get(p + "weight"), sd.get(p + "bias"),
+                     training, momentum, eps)
+    return F.leaky_relu(y, slope)
+
+
+def feature_net(sd, x, training=True, p="feature."):
+    """`networks.py:961-1001` FeatureNet.forward: x [N, 3, H, W] -> [N, 32, H/4, W/4]."""
+    for stage, specs in (("conv0", ((1, 1), (1, 1))), ("conv1", ((2, 2), (1, 1), (1, 1))), ("conv2", ((2, 2), (1, 1), (1, 1)))):
+        for i, (stride, pad) in enumerate(specs):
+            q = f"{p}{stage}.{i}."
+            x = _abn(F.conv2d(x, sd[q + "conv.weight"], None, stride, pad), sd, q + "bn.", training)
+    return F.conv2d(x, sd[p + "toplayer.weight"], sd[p + "toplayer.bias"])
+
+
+def cost_reg_net(sd, x, training=True, p="cost_reg_2."):
+    """`networks.py:1003-1059` CostRegNet.forward: x [1, 41, D, H, W] -> [1, 8, D, H, W]."""
+    c = lambda t, name, stride=1: _abn(F.conv3d(t, sd[f"{p}{name}.conv.weight"], None, stride, 1), sd, f"{p}{name}.bn.", training)
+    up = lambda t, name: _abn(F.conv_transpose3d(t, sd[f"{p}{name}.0.weight"], None, 2, 1, 1), sd, f"{p}{name}.1.", training)
+    conv0 = c(x, "conv0")
+    conv2 = c(c(conv0, "conv1", 2), "conv2")
+    conv4 = c(c(conv2, "conv3", 2), "conv4")
+    x = c(c(conv4, "conv5", 2), "conv6")
+    x = conv4 + up(x, "conv7")
+    x = conv2 + up(x, "conv9")
+    return conv0 + up(x, "conv11")
+
+
+def mvsnet_forward(sd, imgs, proj_mats, near_far, pad=0, training=True):
+    """`networks.py:1142-1238` MVSNet.forward for B = 1 from a state dict: FeatureNet on the V views jointly (batch norm over
+    all of them), 128 depth planes, plane-sweep cost volume, CostRegNet.  Returns (volume_feat, feats, depth_values)."""
+    B, V, _, H, W = imgs.shape
+    feats = feature_net(sd, imgs.reshape(B * V, 3, H, W), training)
+    feats = feats.view(B, V, *feats.shape[1:])
+    t_vals = torch.linspace(0.0, 1.0, steps=128)
+    near, far = near_far
+    depth_values = (near * (1.0 - t_vals) + far * t_vals).unsqueeze(0)
+    cost, _ = cost_volume(imgs, feats, proj_mats, depth_values, pad)
+    return cost_reg_net(sd, cost, training), feats, depth_values

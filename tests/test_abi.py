@@ -42,8 +42,14 @@ def test_new_entry_points_validate_arguments_without_gpu(lib):
     assert lib.zest_sf_smooth_loss_fwd(None, None, 4, 128, 121, 288, 512, 460.8, None, None) == -1
     assert lib.zest_sf_lke_loss_fwd(None, None, None, 4, 128, 115, 288, 512, 460.8, None, None) == -1
     assert lib.zest_project_ndc_fwd(None, None, None, 4, 128, 288, 512, 460.8, None, None) == -1
-    assert lib.zest_cost_volume_fwd(None, None, None, None, 3, 32, 72, 128, 128, 24, None, None, None) == -1
+    assert lib.zest_cost_volume_fwd(None, None, None, None, 3, 32, 72, 128, 128, 24, None, None, 0, 0, None) == -1
     assert b"zest_cost_volume_fwd" in lib.zest_last_error()
+    # the encoding-CNN kernels: channel counts that are not multiples of 4 / 8, unknown kernel shapes, missing statistics
+    assert lib.zest_conv_cl_fwd(None, 1, 8, 8, 4, None, None, 8, 1, 3, 3, 1, None, None, None) == -1
+    assert lib.zest_conv_pack_weights(None, 12, 3, 1, 3, 3, 0, 4, None, None) == -1 and b"multiple of 8" in lib.zest_last_error()
+    assert lib.zest_convt3_cl_fwd(None, 4, 4, 4, 6, None, 8, None, None, None) == -1
+    assert lib.zest_bn_act_cl(None, 10, 8, None, None, None, None, None, 1e-5, 0.1, 0.01, 1, None, None, None) == -1
+    assert lib.zest_resize_bilinear_cl(None, 1, 8, 8, 2, 2, None, None) == -1
     prev = lib.zest_set_gemm_engine(0)          # pure host state: round-trips
     assert lib.zest_set_gemm_engine(prev) == 0
 

@@ -91,3 +91,37 @@ def test_oracle_cost_volume_matches_reference_golden():
     vol, masks = zo.cost_volume(case["imgs"], case["feats"], case["proj_mats"], case["depth_values"], pad=case["pad"])
     assert float((vol - torch.from_numpy(gold["img_feat"])).abs().max()) <= 2e-5
     assert torch.equal(masks, torch.from_numpy(gold["in_masks"]).float())
+
+
+# ----------------------------------------------------------------------------- encoding CNNs ("next" row f3, second half)
+def test_oracle_mvsnet_matches_reference_golden():
+    """oracle.mvsnet_forward (FeatureNet + plane sweep + CostRegNet from a state dict) against the outputs of the unmodified
+    reference MVSNet committed in tests/golden/mvsnet.npz: V = 3 / 4 / 10 views, train-mode batch statistics and eval mode."""
+    import os
+    import numpy as np
+    from tests.golden.make_golden_mvsnet import MVS_CASES, build_mvsnet_case, make_net
+    from zest_nerf_b200 import mvs
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mvsnet.npz"))
+    sd = make_net(mvs.MVSNet).state_dict()
+    with torch.no_grad():
+        for name in MVS_CASES:
+            case = build_mvsnet_case(name)
+            for training in (True, False):
+                tag = f"{name}_{'train' if training else 'eval'}"
+                vol, feats, _ = zo.mvsnet_forward({k: v.clone() for k, v in sd.items()}, case["imgs"], case["proj_mats"], case["near_far"],
+                                                  case["pad"], training)
+                step = int(gold[tag + "__step"])
+                want = torch.from_numpy(gold[tag + "__volume"])
+                assert float((vol[0, :, ::step] - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max())), tag
+                assert float((feats[0] - torch.from_numpy(gold[tag + "__feats"]).float()).abs().max()) <= 2e-2, tag
+
+
+def test_mvsnet_module_mirror_state_dict_keys():
+    """The module mirror carries the reference's parameter names (checkpoints load unchanged): spot-check the key set."""
+    from zest_nerf_b200 import mvs
+    sd = mvs.MVSNet().state_dict()
+    for k in ("feature.conv0.0.conv.weight", "feature.conv1.0.bn.running_var", "feature.toplayer.bias", "cost_reg_2.conv0.conv.weight",
+              "cost_reg_2.conv7.0.weight", "cost_reg_2.conv7.1.running_mean", "cost_reg_2.conv11.1.bias"):
+        assert k in sd, k
+    assert sd["cost_reg_2.conv0.conv.weight"].shape == (8, 41, 3, 3, 3) and sd["cost_reg_2.conv7.0.weight"].shape == (64, 32, 3, 3, 3)
+    assert len(sd) == 92

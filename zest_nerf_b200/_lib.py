@@ -50,7 +50,12 @@ SIGNATURES = {
     "zest_sf_lke_loss_bwd": (_i, [_p, _p, _p, _l, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p]),
     "zest_project_ndc_fwd": (_i, [_p, _p, _p, _l, _i, _i, _i, _f, _p, _p]),
     "zest_project_ndc_bwd": (_i, [_p, _p, _p, _l, _i, _i, _i, _f, _p, _p, _p, _p]),
-    "zest_cost_volume_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "zest_cost_volume_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p]),
+    "zest_conv_pack_weights": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "zest_conv_cl_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "zest_convt3_cl_fwd": (_i, [_p, _i, _i, _i, _i, _p, _i, _p, _p, _p]),
+    "zest_bn_act_cl": (_i, [_p, _l, _i, _p, _p, _p, _p, _p, _f, _f, _f, _i, _p, _p, _p]),
+    "zest_resize_bilinear_cl": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "zest_cost_volume_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "zest_set_gemm_engine": (_i, [_i]),
     "zest_gemm_f32": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _l, _i, _l, _p, _i, _i, _i, _p, _l, _p]),

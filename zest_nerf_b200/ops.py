@@ -103,6 +103,13 @@ def pack_volume(vol):
     return dst
 
 
+def register_packed_volume(vol, vol_cl):
+    """Tell the pack cache that `vol_cl` ([D,H,W,8]) already is the channels-last copy of `vol` ([1,8,D,H,W]): the encoding
+    CNN (mvs.MVSNet) produces both, so `rendering()` / `FrameRenderer` skip the re-layout for its volumes."""
+    src = vol.detach()
+    _vol_cache.insert(_key(src), (src, vol_cl))
+
+
 def pack_images(imgs):
     """[1,V,3,H,W] fp32 -> [V,H,W,4] (cached per tensor version)."""
     if imgs.dim() != 5 or imgs.shape[0] != 1 or imgs.shape[2] != 3:
