@@ -195,7 +195,8 @@ def test_mvsnet_nsff_size_against_oracle(zmvs):
     t_cpu = time.perf_counter() - t0
     net = net.to(DEV)
     d = (imgs.to(DEV), proj.to(DEV), case["near_far"].to(DEV))
-    vol, feats, _ = net(*d, pad=pad)
+    for _ in range(4):           # two eager calls, the CUDA-graph capture, one replay
+        vol, feats, _ = net(*d, pad=pad)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -207,3 +208,32 @@ def test_mvsnet_nsff_size_against_oracle(zmvs):
     print(f"   NSFF-size MVSNet.forward: {e0.elapsed_time(e1) / 3:.2f} ms on the GPU, oracle (torch CPU) {t_cpu:.1f} s; "
           f"volume max|err| {err:.2e} (range {float(want.abs().max()):.2f}), feats max|err| {float((feats.cpu() - want_f).abs().max()):.2e}")
     assert err <= 1e-3 * max(1.0, float(want.abs().max()))
+
+
+def test_mvsnet_cuda_graph_replay_matches_eager(zmvs):
+    """From the third call of a shape on, MVSNet.forward replays a captured CUDA graph: same bits as the eager launches, new
+    inputs are honoured, a changed parameter is re-packed in place (the graph keeps reading the same weight buffer), and the
+    batch-norm running statistics keep moving."""
+    case = build_mvsnet_case("v3")
+    d = lambda c: (c["imgs"].to(DEV), c["proj_mats"].to(DEV), c["near_far"].to(DEV))
+    eager = make_net(zmvs.MVSNet).to(DEV)
+    eager.use_cuda_graph = False
+    net = make_net(zmvs.MVSNet).to(DEV)
+    g = torch.Generator().manual_seed(9)
+    for it in range(5):
+        imgs = case["imgs"] + 0.1 * it * torch.randn(case["imgs"].shape, generator=g)
+        if it == 4:      # an optimiser step between two replays
+            with torch.no_grad():
+                for n_ in (eager, net):
+                    n_.cost_reg_2.conv0.conv.weight.mul_(1.5)
+                    n_.feature.conv0[0].conv.weight.add_(0.01)
+        args = (imgs.to(DEV), case["proj_mats"].to(DEV), case["near_far"].to(DEV))
+        want = eager(*args, pad=case["pad"])
+        got = net(*args, pad=case["pad"])
+        torch.cuda.synchronize()
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1]), f"call {it}"
+    st = next(iter(net._graphs.values()))
+    assert "graph" in st and not st.get("failed"), st.get("failed")
+    assert torch.equal(net.cost_reg_2.conv0.bn.running_mean, eager.cost_reg_2.conv0.bn.running_mean)
+    from zest_nerf_b200 import ops
+    assert torch.equal(ops.pack_volume(got[0]).permute(3, 0, 1, 2)[None], got[0])

@@ -19,7 +19,6 @@
 namespace zest {
 namespace {
 
-constexpr int kVox = 8;    // output positions per thread (along W)
 constexpr int kCo = 8;     // output channels per thread / per weight tile
 constexpr int kConvThreads = 128;
 
@@ -78,8 +77,9 @@ __device__ __forceinline__ void stats_reduce(const float (&s1)[kCo], const float
   }
 }
 
-template <int KD, int KH, int KW, int S>
+template <int KD, int KH, int KW, int S, int VPT>
 __global__ void __launch_bounds__(kConvThreads) conv_cl_kernel(const ConvParams p) {
+  constexpr int kVox = VPT;
   extern __shared__ __align__(16) float w_s[];      // [taps][cin][8] of this block's output-channel tile
   constexpr int taps = KD * KH * KW;
   const int co0 = blockIdx.y * kCo;
@@ -167,7 +167,10 @@ __global__ void __launch_bounds__(kConvThreads) conv_cl_kernel(const ConvParams 
 }
 
 // ConvTranspose3d(k = 3, stride 2, padding 1, output_padding 1): out = 2 x in per dimension; output o gets input i through
-// tap k when o = 2 i - 1 + k.  One thread = 8 outputs of one x parity (ox = 2 (8 xb + j) + px) at (oz, oy) x 8 channels.
+// tap k when o = 2 i - 1 + k: an even o has one tap per dimension (k = 1), an odd o two (k = 0, 2).  One thread = VPT outputs of
+// one parity class (pz, py, px) x 8 channels; the work items are ordered class-major, so a warp walks ONE tap set (1 to 8
+// taps) instead of the masked union of all 27.
+template <int VPT>
 __global__ void __launch_bounds__(kConvThreads) convt3_cl_kernel(const ConvParams p) {
   extern __shared__ __align__(16) float w_s[];
   const int co0 = blockIdx.y * kCo;
@@ -177,21 +180,23 @@ __global__ void __launch_bounds__(kConvThreads) convt3_cl_kernel(const ConvParam
     for (int i = threadIdx.x; i < 27 * p.cin * kCo / 4; i += kConvThreads) dst[i] = __ldg(src + i);
   }
   __syncthreads();
-  const int wblocks = (p.W + kVox - 1) / kVox;           // blocks of 8 same-parity outputs = 8 input columns
-  const int64_t items = (int64_t)p.No * p.Ho * 2 * wblocks;
+  const int wblocks = (p.W + VPT - 1) / VPT;           // blocks of VPT same-parity outputs = VPT input columns
+  const int64_t per_class = (int64_t)p.N * p.H * wblocks;
   const int64_t item = (int64_t)blockIdx.x * kConvThreads + threadIdx.x;
-  float acc[kVox][kCo];
+  float acc[VPT][kCo];
 #pragma unroll
-  for (int v = 0; v < kVox; ++v)
+  for (int v = 0; v < VPT; ++v)
 #pragma unroll
     for (int j = 0; j < kCo; ++j) acc[v][j] = 0.f;
-  const bool active = item < items;
+  const bool active = item < 8 * per_class;
   int oz = 0, oy = 0, px = 0, xb = 0;
   if (active) {
-    xb = (int)(item % wblocks);
-    int64_t r = item / wblocks;
-    px = (int)(r & 1); r >>= 1;
-    oy = (int)(r % p.Ho); oz = (int)(r / p.Ho);
+    const int cls = (int)(item / per_class);
+    int64_t r = item - (int64_t)cls * per_class;
+    xb = (int)(r % wblocks); r /= wblocks;
+    const int hy = (int)(r % p.H), hz = (int)(r / p.H);
+    px = cls & 1;
+    oy = 2 * hy + ((cls >> 1) & 1); oz = 2 * hz + ((cls >> 2) & 1);
     const int cq = p.cin >> 2;
     for (int kd = 0; kd < 3; ++kd) {
       if (((oz + 1 - kd) & 1) != 0) continue;
@@ -204,13 +209,13 @@ __global__ void __launch_bounds__(kConvThreads) convt3_cl_kernel(const ConvParam
         const float4* row = reinterpret_cast<const float4*>(p.x + ((int64_t)iz * p.H + iy) * p.W * p.cin);
         for (int kw = 0; kw < 3; ++kw) {
           if (((px + 1 - kw) & 1) != 0) continue;
-          const int dx = (px + 1 - kw) >> 1;        // ix = (ox + 1 - kw) / 2 = 8 xb + j + dx
+          const int dx = (px + 1 - kw) >> 1;        // ix = (ox + 1 - kw) / 2 = VPT xb + j + dx
           const float4* wrow = reinterpret_cast<const float4*>(w_s) + (int64_t)((kd * 3 + kh) * 3 + kw) * p.cin * 2;
           for (int q = 0; q < cq; ++q) {
             const float4* wq = wrow + (int64_t)(4 * q) * 2;
 #pragma unroll
-            for (int v = 0; v < kVox; ++v) {
-              const int ix = xb * kVox + v + dx;
+            for (int v = 0; v < VPT; ++v) {
+              const int ix = xb * VPT + v + dx;
               const float4 in = (ix >= 0 && ix < p.W) ? __ldg(row + (int64_t)ix * cq + q) : make_float4(0.f, 0.f, 0.f, 0.f);
               fma_vox(acc[v], in, wq);
             }
@@ -224,8 +229,8 @@ __global__ void __launch_bounds__(kConvThreads) convt3_cl_kernel(const ConvParam
   for (int j = 0; j < kCo; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   if (active) {
 #pragma unroll
-    for (int v = 0; v < kVox; ++v) {
-      const int ox = 2 * (xb * kVox + v) + px;
+    for (int v = 0; v < VPT; ++v) {
+      const int ox = 2 * (xb * VPT + v) + px;
       if (ox >= p.Wo) break;
 #pragma unroll
       for (int j = 0; j < kCo; ++j) { s1[j] += acc[v][j]; s2[j] = fmaf(acc[v][j], acc[v][j], s2[j]); }
@@ -309,16 +314,25 @@ __global__ void resize_bilinear_cl_kernel(const float4* __restrict__ x, int V, i
   }
 }
 
-template <int KD, int KH, int KW, int S>
-int launch_conv(const ConvParams& p, cudaStream_t st) {
+template <int KD, int KH, int KW, int S, int VPT>
+int launch_conv_vpt(const ConvParams& p, cudaStream_t st) {
   const size_t smem = (size_t)KD * KH * KW * p.cin * kCo * sizeof(float);
   ZEST_CHECK_ARG(smem <= 200 * 1024, "zest_conv_cl_fwd: weight tile of %zu bytes does not fit shared memory", smem);
-  ZEST_CUDA(cudaFuncSetAttribute(conv_cl_kernel<KD, KH, KW, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t items = (int64_t)p.No * p.Ho * ((p.Wo + kVox - 1) / kVox);
+  ZEST_CUDA(cudaFuncSetAttribute(conv_cl_kernel<KD, KH, KW, S, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t items = (int64_t)p.No * p.Ho * ((p.Wo + VPT - 1) / VPT);
   dim3 grid((unsigned)((items + kConvThreads - 1) / kConvThreads), (unsigned)(p.cout / kCo));
-  conv_cl_kernel<KD, KH, KW, S><<<grid, kConvThreads, smem, st>>>(p);
+  conv_cl_kernel<KD, KH, KW, S, VPT><<<grid, kConvThreads, smem, st>>>(p);
   ZEST_LAUNCH_CHECK();
   return ZEST_OK;
+}
+
+// 8 outputs per thread amortise the weight fetches best, but the coarse levels of the U-Net have too few outputs to fill
+// 148 SMs that way (CostRegNet.conv5: 48 blocks): below ~2 blocks per SM the layer runs with 2 outputs per thread instead.
+template <int KD, int KH, int KW, int S>
+int launch_conv(const ConvParams& p, cudaStream_t st) {
+  const int64_t blocks8 = ((int64_t)p.No * p.Ho * ((p.Wo + 7) / 8) + kConvThreads - 1) / kConvThreads * (p.cout / kCo);
+  if (blocks8 >= 2 * (int64_t)num_sms()) return launch_conv_vpt<KD, KH, KW, S, 8>(p, st);
+  return launch_conv_vpt<KD, KH, KW, S, 2>(p, st);
 }
 
 }  // namespace
@@ -375,10 +389,18 @@ extern "C" int zest_convt3_cl_fwd(const float* x, int D, int H, int W, int cin, 
   const size_t smem = (size_t)27 * cin * kCo * sizeof(float);
   ZEST_CHECK_ARG(smem <= 200 * 1024, "zest_convt3_cl_fwd: weight tile does not fit shared memory");
   if (stats) ZEST_CUDA(cudaMemsetAsync(stats, 0, 2 * (size_t)cout * sizeof(double), st));
-  ZEST_CUDA(cudaFuncSetAttribute(convt3_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t items = (int64_t)p.No * p.Ho * 2 * ((W + kVox - 1) / kVox);
-  dim3 grid((unsigned)((items + kConvThreads - 1) / kConvThreads), (unsigned)(cout / kCo));
-  convt3_cl_kernel<<<grid, kConvThreads, smem, st>>>(p);
+  const int64_t blocks8 = ((int64_t)8 * D * H * ((W + 7) / 8) + kConvThreads - 1) / kConvThreads * (cout / kCo);
+  if (blocks8 >= 2 * (int64_t)num_sms()) {
+    ZEST_CUDA(cudaFuncSetAttribute(convt3_cl_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t items = (int64_t)8 * D * H * ((W + 7) / 8);
+    dim3 grid((unsigned)((items + kConvThreads - 1) / kConvThreads), (unsigned)(cout / kCo));
+    convt3_cl_kernel<8><<<grid, kConvThreads, smem, st>>>(p);
+  } else {
+    ZEST_CUDA(cudaFuncSetAttribute(convt3_cl_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t items = (int64_t)8 * D * H * ((W + 1) / 2);
+    dim3 grid((unsigned)((items + kConvThreads - 1) / kConvThreads), (unsigned)(cout / kCo));
+    convt3_cl_kernel<2><<<grid, kConvThreads, smem, st>>>(p);
+  }
   ZEST_LAUNCH_CHECK();
   return ZEST_OK;
 }

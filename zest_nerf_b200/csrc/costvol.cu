@@ -81,12 +81,16 @@ __global__ void __launch_bounds__(256) cost_volume_kernel(const float* __restric
                                                           int H, int W, int D, int pad, int cpad, float* __restrict__ img_feat,
                                                           float* __restrict__ in_masks) {
   __shared__ float s_proj[kMaxSrc * 12];
+  // channels-last output: every warp assembles its 32 voxels x cpad floats here and stores them as one contiguous run
+  __shared__ __align__(16) float s_out[CL ? 8 * 32 * (12 + 4 * CQ) : 4];
   load_proj(proj, nsrc, s_proj);
   constexpr int C = 4 * CQ;
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
   const int64_t plane = (int64_t)Hp * Wp, vol = plane * D;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= vol) return;
+  const int64_t idx_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (!CL && idx_raw >= vol) return;
+  const bool live = idx_raw < vol;
+  const int64_t idx = live ? idx_raw : vol - 1;      // CL: a dead lane recomputes the last voxel and only helps with the stores
   const int d = (int)(idx / plane);
   const int rem = (int)(idx - (int64_t)d * plane);
   const int y = rem / Wp, x = rem - y * Wp;
@@ -120,7 +124,8 @@ __global__ void __launch_bounds__(256) cost_volume_kernel(const float* __restric
     if (!CL && in_masks) in_masks[(int64_t)(v + 1) * vol + idx] = tap.mask;
     if (v < 2) {
       const float4 cv = tap4(imgs_cl + (int64_t)(v + 1) * H * W * 4, 4, tap);
-      img9[3 * v + 3] = cv.x; img9[3 * v + 4] = cv.y; img9[3 * v + 5] = cv.z;
+      if (v == 0) { img9[3] = cv.x; img9[4] = cv.y; img9[5] = cv.z; }     // static indices: img9 stays in registers
+      else { img9[6] = cv.x; img9[7] = cv.y; img9[8] = cv.z; }
     }
     const float* fv = feats_cl + (int64_t)(v + 1) * vstride;
 #pragma unroll
@@ -142,8 +147,10 @@ __global__ void __launch_bounds__(256) cost_volume_kernel(const float* __restric
     var[4 * q + 3] = __fsub_rn(__fmul_rn(sq[q].w, inv), __fmul_rn(mw, mw));
   }
   if (CL) {
-    float4* o = reinterpret_cast<float4*>(img_feat + idx * cpad);
-    float row[12 + C];     // [9 image channels | C variances | zero pad], written as cpad / 4 vectors
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cq = cpad >> 2;
+    float4* mine = reinterpret_cast<float4*>(s_out) + (warp * 32 + lane) * cq;
+    float row[12 + C];     // [9 image channels | C variances | zero pad], cpad / 4 vectors
 #pragma unroll
     for (int i = 0; i < 9; ++i) row[i] = img9[i];
 #pragma unroll
@@ -151,7 +158,13 @@ __global__ void __launch_bounds__(256) cost_volume_kernel(const float* __restric
     row[9 + C] = 0.f; row[10 + C] = 0.f; row[11 + C] = 0.f;
 #pragma unroll
     for (int i = 0; i < (12 + C) / 4; ++i)
-      if (4 * i < cpad) o[i] = make_float4(row[4 * i], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
+      if (i < cq) mine[i] = make_float4(row[4 * i], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
+    __syncwarp();
+    const int64_t warp_base = idx_raw - lane;                       // first voxel of this warp
+    const int64_t n_live = vol - warp_base < 32 ? vol - warp_base : 32;
+    const float4* src = reinterpret_cast<const float4*>(s_out) + warp * 32 * cq;
+    float4* dst = reinterpret_cast<float4*>(img_feat) + warp_base * cq;
+    for (int e = lane; e < (int)n_live * cq; e += 32) dst[e] = src[e];  // 32 lanes x 16 B contiguous per instruction
   } else {
 #pragma unroll
     for (int i = 0; i < 9; ++i) img_feat[(int64_t)i * vol + idx] = img9[i];

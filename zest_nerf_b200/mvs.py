@@ -141,6 +141,7 @@ class _Act:
 
 
 _wcache = {}
+_conv_log = None      # when a list: every (conv, cin_pad, transposed) a forward touches (recorded while a graph is captured)
 
 
 def _packed_weight(conv, cin_pad, transposed=False):
@@ -158,7 +159,11 @@ def _packed_weight(conv, cin_pad, transposed=False):
         cout, cin = wd.shape[:2]
     k = tuple(wd.shape[2:])
     kd, kh, kw = (1,) * (3 - len(k)) + k
-    packed = torch.empty((cout // 8, kd * kh * kw, cin_pad, 8), device=wd.device, dtype=torch.float32)
+    shape = (cout // 8, kd * kh * kw, cin_pad, 8)
+    if hit is not None and hit[2] is conv and tuple(hit[1].shape) == shape and hit[1].device == wd.device:
+        packed = hit[1]      # refreshed IN PLACE: a captured CUDA graph of the forward keeps reading this buffer
+    else:
+        packed = torch.empty(shape, device=wd.device, dtype=torch.float32)
     _lib.check(_lib.load().zest_conv_pack_weights(_ptr(wd), cout, cin, kd, kh, kw, int(transposed), cin_pad, _ptr(packed), _stream()),
                "zest_conv_pack_weights")
     _wcache[key] = (state, packed, conv)
@@ -175,6 +180,8 @@ def _conv(x: _Act, conv, bn=None, training=True, skip=None, out=None):
     kd, kh, kw = (1,) * (3 - len(k)) + k
     stride = conv.stride[0]
     packed = _packed_weight(conv, x.C, transposed)
+    if _conv_log is not None:
+        _conv_log.append((conv, x.C, transposed))
     dev = x.t.device
     stats = torch.empty((2 * cout,), device=dev, dtype=torch.float64) if (bn is not None and training) else None
     if transposed:
@@ -292,14 +299,61 @@ class MVSNet(nn.Module):
     def build_volume_cost(self, imgs, feats, proj_mats, depth_values, pad=0):
         return build_volume_cost(imgs, feats, proj_mats, depth_values, pad=pad)
 
+    use_cuda_graph = True      # replay the ~80 launches of a forward as one CUDA graph from the third call of a given shape on
+
     @torch.no_grad()
     def forward(self, imgs, proj_mats, near_far, pad=0, return_color=False, lindisp=False, vis_test=False, test_dir=None):
         if vis_test:
             raise NotImplementedError("vis_test (activation dumps to disk) is not provided by the B200 path")
         imgs = _f32c(imgs, "imgs")
-        B, V, _, H, W = imgs.shape
-        if B != 1:
+        if imgs.shape[0] != 1:
             raise RuntimeError("MVSNet: batch size must be 1")
+        if self.use_cuda_graph and not return_color and torch.is_tensor(near_far) and near_far.is_cuda \
+                and not torch.cuda.is_current_stream_capturing():
+            out = self._forward_graphed(imgs, proj_mats, near_far, int(pad), bool(lindisp))
+            if out is not None:
+                return out
+        return self._forward_eager(imgs, proj_mats, near_far, pad, return_color, lindisp)
+
+    def _forward_graphed(self, imgs, proj_mats, near_far, pad, lindisp):
+        """The forward is launch-bound on the host (4.3 ms of kernels, ~80 launches): captured once per (shape, mode) and
+        replayed.  Inputs are copied into the graph's static buffers, outputs are cloned out of them; weights are re-packed in
+        place when a parameter changed, batch-norm running statistics are updated by the captured kernels themselves."""
+        global _conv_log
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        key = (tuple(imgs.shape), tuple(proj_mats.shape), pad, lindisp, self.training, imgs.device)
+        st = self._graphs.setdefault(key, {"calls": 0})
+        st["calls"] += 1
+        if st.get("failed") or st["calls"] < 3:
+            return None                       # the first two calls run eagerly (lazy kernel loading, caches, allocator warm-up)
+        if "graph" not in st:
+            try:
+                ins = (imgs.clone(), proj_mats.detach().to(imgs.device, torch.float32).clone(), near_far.detach().to(torch.float32).clone())
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize(imgs.device)
+                _conv_log = []
+                try:
+                    with torch.cuda.graph(g):
+                        outs = self._forward_eager(ins[0], ins[1], ins[2], pad, False, lindisp, register=False)
+                    convs = list(_conv_log)
+                finally:
+                    _conv_log = None
+                st.update(graph=g, ins=ins, outs=outs, convs=convs, vol_cl=self._last_vol_cl)
+            except Exception as e:            # anything the capture cannot take: stay eager, remember why
+                st["failed"] = f"{type(e).__name__}: {e}"[:300]
+                return None
+        for conv, cin_pad, transposed in st["convs"]:
+            _packed_weight(conv, cin_pad, transposed)
+        a, b, c = st["ins"]
+        a.copy_(imgs); b.copy_(proj_mats); c.copy_(near_far)
+        st["graph"].replay()
+        vol, feats, depth = (t.clone() for t in st["outs"])
+        ops.register_packed_volume(vol, st["vol_cl"].clone())
+        return vol, feats, depth
+
+    def _forward_eager(self, imgs, proj_mats, near_far, pad=0, return_color=False, lindisp=False, register=True):
+        B, V, _, H, W = imgs.shape
         dev = imgs.device
         lib = _lib.load()
         with torch.cuda.device(dev):
@@ -326,5 +380,7 @@ class MVSNet(nn.Module):
             vol_cl, _ = self.cost_reg_2.forward_cl(cost_cl)                      # [D, Hp, Wp, 8]: the gather's layout
             volume_feat = torch.zeros((1, 8, D, Hp, Wp), device=dev, dtype=torch.float32)    # the unpack kernel accumulates
             _lib.check(lib.zest_unpack_volume_grad(_ptr(vol_cl.t), _ptr(volume_feat), D, Hp, Wp, _stream()), "zest_unpack_volume")
-            ops.register_packed_volume(volume_feat, vol_cl.t)
+            self._last_vol_cl = vol_cl.t
+            if register:
+                ops.register_packed_volume(volume_feat, vol_cl.t)
         return volume_feat, feats, depth_values
