@@ -45,6 +45,8 @@ def _cl(x):
     ("3d", 8, 16, 3, 2, (8, 8, 16)),
     ("3d", 16, 32, 3, 2, (5, 7, 9)),        # odd sizes under stride 2
     ("3d", 64, 64, 3, 1, (2, 3, 5)),
+    ("3d", 12, 8, 3, 1, (40, 50, 150)),     # enough blocks for the 8-positions-per-thread variant, ragged last W block
+    ("3d", 8, 16, 3, 1, (34, 33, 70)),      # same, two output-channel tiles
     ("3dT", 64, 32, 3, 2, (2, 3, 5)),       # transposed: k 3, s 2, p 1, output_padding 1
     ("3dT", 16, 8, 3, 2, (4, 5, 12)),
 ])

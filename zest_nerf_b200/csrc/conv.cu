@@ -14,6 +14,10 @@
 // validation, networks.py:626) are reduced in the same kernel: warp shuffle -> shared -> one double atomicAdd per block
 // and channel.  bn_act_cl_kernel then normalises, applies leaky ReLU and (U-Net skips) adds the already-activated skip
 // tensor in one pass.  Transposed convolutions (k 3, s 2, p 1, output_padding 1) are gathered per output parity class.
+// Tried and removed (round 2, same-box A/B): staging the 3 x 18 x 66 input halo of a 16 x 64 output tile through shared
+// memory four channels at a time (cp.async, conflict-free padded rows, two blocks per SM).  It cut conv0's L2 traffic from
+// 22x to 3.5x the input, but its eleven load -> barrier -> compute phases per tile were not hidden by the second block:
+// 1.67 ms against 1.45 ms for the L1-path kernel below.
 #include "common.cuh"
 
 namespace zest {

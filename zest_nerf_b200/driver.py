@@ -327,7 +327,8 @@ class FrameRenderer:
     def gather_maps(self, maps, n_rays, dst=0, keys=None):
         """Collect each rank's slab of every per-ray map: ONE all-gather of a packed [rays / world (padded), sum of map
         widths] tensor into a persistent buffer.  The key list is rank-independent (`keys`, default: the maps this
-        renderer produces), so a rank with an empty slab still takes part in the collective."""
+        renderer produces), so a rank with an empty slab still takes part in the collective.  The returned maps are views
+        of that persistent buffer: they are valid until the next `gather_maps` call (clone them to keep a frame)."""
         if not (self.dist and self.world > 1):
             return maps
         if keys is None:

@@ -20,6 +20,7 @@ itself is differentiable wrt the feature maps).
 from __future__ import annotations
 
 import ctypes as C_
+import weakref
 
 import torch
 import torch.nn as nn
@@ -140,16 +141,16 @@ class _Act:
         self.N, self.H, self.W, self.C = t.shape
 
 
-_wcache = {}
+_wcache = weakref.WeakKeyDictionary()      # conv module -> {cin_pad: (parameter state, packed weights)}; dies with the module
 _conv_log = None      # when a list: every (conv, cin_pad, transposed) a forward touches (recorded while a graph is captured)
 
 
 def _packed_weight(conv, cin_pad, transposed=False):
     """Repacked copy of a conv weight, rebuilt when the parameter changes (same idea as ops.PackedNet)."""
     w = conv.weight
-    key = (id(conv), cin_pad)
     state = (w.data_ptr(), w._version, w.device)
-    hit = _wcache.get(key)
+    per_conv = _wcache.setdefault(conv, {})
+    hit = per_conv.get(cin_pad)
     if hit is not None and hit[0] == state:
         return hit[1]
     wd = _f32c(w.detach(), "conv weight")
@@ -160,13 +161,13 @@ def _packed_weight(conv, cin_pad, transposed=False):
     k = tuple(wd.shape[2:])
     kd, kh, kw = (1,) * (3 - len(k)) + k
     shape = (cout // 8, kd * kh * kw, cin_pad, 8)
-    if hit is not None and hit[2] is conv and tuple(hit[1].shape) == shape and hit[1].device == wd.device:
+    if hit is not None and tuple(hit[1].shape) == shape and hit[1].device == wd.device:
         packed = hit[1]      # refreshed IN PLACE: a captured CUDA graph of the forward keeps reading this buffer
     else:
         packed = torch.empty(shape, device=wd.device, dtype=torch.float32)
     _lib.check(_lib.load().zest_conv_pack_weights(_ptr(wd), cout, cin, kd, kh, kw, int(transposed), cin_pad, _ptr(packed), _stream()),
                "zest_conv_pack_weights")
-    _wcache[key] = (state, packed, conv)
+    per_conv[cin_pad] = (state, packed)
     return packed
 
 
@@ -351,6 +352,10 @@ class MVSNet(nn.Module):
         vol, feats, depth = (t.clone() for t in st["outs"])
         ops.register_packed_volume(vol, st["vol_cl"].clone())
         return vol, feats, depth
+
+    def release_graphs(self):
+        """Drop the captured CUDA graphs and their static buffers (about 1 GB per NSFF-size shape)."""
+        self._graphs = {}
 
     def _forward_eager(self, imgs, proj_mats, near_far, pad=0, return_color=False, lindisp=False, register=True):
         B, V, _, H, W = imgs.shape
