@@ -177,10 +177,15 @@ def test_forward_val_with_the_cuda_encoders_too(lib):
     try:
         for mods, enc_cls in ((ref, ref.networks.MVSNet), (pat, mvs.MVSNet)):
             nw = mods.networks
-            sc = make_scene(H=32, W=64, V=3, pad=4, D=128, dynamic=True, seed=43, spread=2.0, net_cls=nw.MVSNeRF, emb_cls=nw.Embedding)
+            sc = make_scene(H=32, W=64, V=3, pad=4, D=128, dynamic=True, seed=43, spread=2.0, net_cls=nw.MVSNeRF, emb_cls=nw.Embedding,
+                            opaque=True)      # alpha bias + 3: both nets render something
             args = _args(sc)
-            gen = nw.DyMVSNeRF_G(args, 30, sc.net_dynamic, sc.net_static, make_net(enc_cls, seed=7), make_net(enc_cls, seed=8),
-                                 sc.emb_pts, sc.emb_xyzt, sc.emb_dir).to(DEV)
+            encs = [make_net(enc_cls, seed=7), make_net(enc_cls, seed=8)]
+            with torch.no_grad():      # random-init encoders emit volumes of range ~20, which the multiplicative gate of the
+                for enc in encs:       # random-init MLP raises to the 8th power: scale the two output norms to a trained net's O(1)
+                    for bn in (enc.cost_reg_2.conv0.bn, enc.cost_reg_2.conv11[1]):
+                        bn.weight.mul_(0.05); bn.bias.mul_(0.05)
+            gen = nw.DyMVSNeRF_G(args, 30, sc.net_dynamic, sc.net_static, encs[0], encs[1], sc.emb_pts, sc.emb_xyzt, sc.emb_dir).to(DEV)
             x = _batch(sc, torch.Generator().manual_seed(3))
             # relative projections of nearby cameras at feature resolution (data/nsff.py:299,318), 3 neighbour frames for the
             # dynamic encoder of this test (its cost volume has 9 + 32 channels for any number of views)
@@ -195,9 +200,13 @@ def test_forward_val_with_the_cuda_encoders_too(lib):
     torch.cuda.synchronize()
     want, got = outs
     names = ("rgbs_blend", "depths_blend", "rgbs_rig", "depths_rig", "rgbs_dy", "depths_dy", "weights_dd")
-    # two stages compound here: the encoders' volumes differ by ~3e-5 (different fp32 summation orders of the convolutions),
-    # which the radiance MLP and the compositing amplify; colours / weights keep the 2e-3 bar, depths (range 2..6) get 1e-2
+    # two stages compound here (the encoders' volumes differ by ~1e-5: different fp32 summation orders of the convolutions);
+    # on this conditioned scene every map still keeps the 2e-3 bar (measured <= 1.1e-4)
+    errs = {}
     for name, w_list, g_list in zip(names, want[1:], got[1:]):
         w, g_ = torch.cat(w_list), torch.cat(g_list)
-        err = float((g_ - w).abs().max())
-        assert err <= (1e-2 if "depth" in name else 2e-3), f"{name}: max|err| {err:.3e}"
+        errs[name] = float((g_ - w).abs().max())
+    print("   forward_val with CUDA encoders + drop-in renderer vs the reference: " + ", ".join(f"{k} {v:.1e}" for k, v in errs.items()))
+    assert float(torch.cat(want[5]).abs().max()) > 0 and float(torch.cat(want[7]).max()) > 0, "degenerate scene: the dynamic net renders nothing"
+    for name, err in errs.items():
+        assert err <= 2e-3, f"{name}: max|err| {err:.3e}"

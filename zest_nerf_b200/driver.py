@@ -125,8 +125,9 @@ class FrameRenderer:
     def _ensure_slots(self, layout):
         if self._layout_key == layout.key():
             return
-        if self.cuda:
-            torch.cuda.current_stream(self.device).synchronize()     # a layout change is rare: drain users of the old slots
+        if self.cuda:                                                 # a layout change is rare: drain every user of the old slots
+            torch.cuda.current_stream(self.device).synchronize()
+            self.side.synchronize()
         self._slots = [FrameSlot(layout, self.device), FrameSlot(layout, self.device)]
         self._layout_key, self._peer, self._handles, self._cur, self._pending = layout.key(), {}, None, 0, None
         if self.cuda and self.dist and self.world > 1:
@@ -189,7 +190,10 @@ class FrameRenderer:
                 lib = _lib.load()
                 t = slot.t
                 V = layout.V
-                f32 = lambda x, n: ops._f32c(x.detach().to(self.device), n)
+                def f32(x, n):
+                    x = ops._f32c(x.detach().to(self.device), n)
+                    x.record_stream(self.side)        # produced on the render stream, read by the pack kernels on the side stream
+                    return x
                 _lib.check(lib.zest_pack_volume(ops._ptr(f32(vol_static, "vol_static")), ops._ptr(t["vol_s"]), layout.D, layout.Hv,
                                                 layout.Wv, ops._stream()), "zest_pack_volume")
                 _lib.check(lib.zest_pack_images(ops._ptr(f32(imgs, "imgs")), ops._ptr(t["img"]), V, layout.H, layout.W, ops._stream()),
