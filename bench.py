@@ -195,6 +195,7 @@ def parity_report(kept, sc, dev, cfg):
                                          8 + 4 * sc.V, want_idx=True)
             rep["idx_mismatches"] += int((vox.cpu() != vox_w).sum()) + int((pix.cpu() != pix_w.reshape(R * S, sc.V, 2).int()).sum())
             rep["indices_checked"] += vox_w.numel() + pix_w.numel()
+            rep["ref_rgb_map_absmax"] = max(rep.get("ref_rgb_map_absmax", 0.0), float(want["rgb_map"].abs().max()))
             for mode in ("fp32", "bf16"):
                 with ops.mlp_mode(mode):
                     got = rendering(sc.args, *d, **sc.render_kwargs())
@@ -203,10 +204,16 @@ def parity_report(kept, sc, dev, cfg):
                     rep["max_abs_" + mode] = max(rep["max_abs_" + mode], float(diff.abs().max()))
                     if mode == "bf16" and k in se:
                         se[k][0] += float((diff.double() ** 2).sum()); se[k][1] += diff.numel()
+                # the per-sample network outputs and gathered features too: a random-init static net can render an empty map
+                # (sigma <= 0 everywhere), which would make the map comparison vacuous on a static-only config
+                for k in ("raw_rgba", "input_feat"):
+                    key = f"max_abs_{mode}_{k}"
+                    rep[key] = max(rep.get(key, 0.0), float((got[k].cpu() - want[k]).abs().max()))
     for k, (s2, n) in se.items():
         if n:
             rep["psnr_bf16_vs_reference_" + k] = 99.0 if s2 == 0 else -10.0 * math.log10(s2 / n)
-    rep["bars"] = "indices bit-exact; fp32 MLP <= 2e-3 max-abs on every map; bf16: PSNR vs the reference's fp32 render"
+    rep["bars"] = ("indices bit-exact; fp32 MLP <= 2e-3 max-abs on every map (and raw_rgba / input_feat per sample); "
+                   "bf16: PSNR vs the reference's fp32 render")
     return rep
 
 
@@ -502,6 +509,46 @@ def mvsnet_stage(dev, pk, reps=5):
             "gmac": (macs + fmacs) / 1e9, "achieved_fp32_tflops": tf, "fp32_fma_peak_tflops_nominal": peak, "frac_of_fp32_fma_peak": tf / peak,
             "launch_mode": graph_state, "volume_shape": list(vol.shape), "hbm_floor_ms": (vox * 44 * 4 * 2 + vox * 8 * 4 * 6) / (pk["hbm_gbs"] * 1e6),
             "note": "exact-fp32 CUDA-core convolutions (the reference's CPU arithmetic; cuDNN would use TF32): bound by FMA issue, not HBM"}
+
+
+def frame_pipeline_stage(sc, fr, job, dev, R, reps=5):
+    """The whole per-frame pipeline of test.py on one GPU: both encoding volumes from the source / neighbour images
+    (mvs.MVSNet.forward x 2: static + dynamic encoder), then the ray-path render of the full frame from them (the volumes go
+    from the CNN to the gather in channels-last form, no re-layout).  rays/s of that pipeline = frame rays / total time."""
+    import torch
+    from zest_nerf_b200 import mvs
+    g = torch.Generator(device=dev).manual_seed(4)
+    enc_s, enc_d = mvs.MVSNet().to(dev), mvs.MVSNet().to(dev)
+    with torch.no_grad():      # random-init encoders emit volumes of range ~20; a trained net's are O(1)
+        for enc in (enc_s, enc_d):
+            for bn in (enc.cost_reg_2.conv0.bn, enc.cost_reg_2.conv11[1]):
+                bn.weight.mul_(0.05); bn.bias.mul_(0.05)
+    V = sc.imgs.shape[1] - 1
+    proj_s = torch.eye(4, device=dev)[:3][None, None].repeat(1, V, 1, 1)
+    proj_d = torch.eye(4, device=dev)[:3][None, None].repeat(1, 4, 1, 1)
+    for v in range(1, V):
+        proj_s[0, v, 0, 3] = 6.0 * v
+    for v in range(1, 4):
+        proj_d[0, v, 0, 3] = -5.0 * v
+    nf = sc.near_fars[0, 0].to(dev)
+    imgs_s, imgs_d = (sc.imgs[:, :-1] - 0.45) / 0.225, (sc.nb_imgs - 0.45) / 0.225
+    src_imgs = sc.imgs[:, :-1].contiguous()
+
+    def once():
+        vol_s, _, _ = enc_s(imgs_s, proj_s, nf, pad=24)
+        vol_d, _, _ = enc_d(imgs_d, proj_d, nf, pad=24)
+        fr.set_frame(vol_s, src_imgs, sc.im_cam_mat, vol_d, sc.nb_imgs, sc.nb_cam_mat)
+        return fr.render_rays(*job.d, job.t_ref)
+    for _ in range(4):
+        out = once()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(reps):
+        out = once()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"what": "2 x MVSNet.forward (static + dynamic encoding volume from 3 + 4 views of 288 x 512) + frame install + full-frame render",
+            "ms_per_frame": ms, "rays_per_s": R / ms * 1e3, "finite": bool(torch.isfinite(out["rgb_map_ref"]).all())}
 
 
 FT_ENGINE_NAMES = {0: "fp32 CUDA cores (sgemm)", 1: "tcgen05 3 x bf16, one accumulator", 2: "tcgen05 3 x tf32, split accumulators (default)"}
@@ -1053,6 +1100,12 @@ def main():
             f3b = mvsnet_stage(dev, pk)
         except Exception as e:
             f3b = {"error": f"{type(e).__name__}: {e}"[:300]}
+    pipe = None
+    if rank == 0 and world == 1 and c["dynamic"] and not args.no_fine_tune:
+        try:
+            pipe = frame_pipeline_stage(sc, fr, job, dev, R)
+        except Exception as e:
+            pipe = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -1088,7 +1141,7 @@ def main():
                 "steps_ms": [round(x, 3) for x in ms], "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 3), "clocks": clocks, "roofline": roofline, "e2e": e2e,
                 "cpu_baseline": cpu, "parity": parity, "torch_gpu_baseline": tgpu, "sharded_frame_equals_single_gpu": sharded_ok,
                 "pose_parallel_weak": pose_parallel, "cfg3_strong": cfg3_strong,
-                "gather_stage": gstage, "fine_tune": ft, "next_rows": {"f1_ray_builder": f1, "f3_cost_volume": f3, "f3_mvsnet": f3b, "f4_sf_losses": f4}}
+                "gather_stage": gstage, "fine_tune": ft, "next_rows": {"f1_ray_builder": f1, "f3_cost_volume": f3, "f3_mvsnet": f3b, "f4_sf_losses": f4, "full_frame_pipeline": pipe}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
