@@ -191,6 +191,11 @@ int zest_project_ndc_fwd(const float* w2c, const float* weights, const float* ra
 int zest_project_ndc_bwd(const float* w2c, const float* weights, const float* raw_pts, int64_t R, int S, int H, int W,
                          float f, const float* g_pts_2d, float* g_weights, float* g_raw_pts, void* stream);
 
+/* ---- frame driver: peer copy ---------------------------------------------------------------
+ * cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault) on `stream`: `src` may be another GPU's buffer mapped through CUDA IPC
+ * (driver.FrameRenderer's "ipc" transport pulls the source rank's packed frame slot with it). */
+int zest_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream);
+
 /* ---- plane-sweep cost volume ("next" row f3, first half) ---------------------------------------------
  * networks.py:1077-1140 MVSNet.build_volume_cost + utils.py:49-99 homo_warp in one pass.
  * feats_cl [V, C/4, H, W, 4] feature maps as planes of channel quads (view 0 = reference, C in {4, 8, 16, 32}), imgs_cl [V, H, W, 4]

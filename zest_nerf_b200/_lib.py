@@ -20,6 +20,7 @@ SIGNATURES = {
     "zest_last_error": (C.c_char_p, []),
     "zest_version": (_i, []),
     "zest_launch_count": (_l, []),
+    "zest_memcpy_async": (_i, [_p, _p, _l, _p]),
     "zest_pack_volume": (_i, [_p, _p, _i, _i, _i, _p]),
     "zest_pack_images": (_i, [_p, _p, _i, _i, _i, _p]),
     "zest_unpack_volume_grad": (_i, [_p, _p, _i, _i, _i, _p]),

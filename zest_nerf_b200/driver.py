@@ -10,10 +10,12 @@ transports:
             shares the SMs with the render kernel of the current frame, which is why that kernel claims its tiles
             dynamically (csrc/mlp_tc.cu): a CTA that starts late or loses its SM for a while just renders fewer tiles.
   * "ipc":  every rank maps the source rank's slot through CUDA IPC once and pulls it with a peer-to-peer
-            `cudaMemcpyAsync` (copy engines: no SM taken); two one-element NCCL all-reduces on the side stream order the
-            pull against the source's pack kernels.  Stand-alone it is the faster transport (0.37 vs 0.6 ms for 190 MB
-            between two B200s), pipelined under a render it measured slower (the receiving rank's render is enqueued
-            late), so it is opt-in (`transport="ipc"` / ZEST_FRAME_TRANSPORT=ipc).
+            `cudaMemcpyAsync` on its own side stream (copy engines: no SM taken); two one-element NCCL all-reduces on the
+            side stream order the pull against the source's pack kernels.  Measured: stand-alone 0.44 vs 0.62 ms for
+            190 MB between two B200s, and 3 % faster than NCCL in the pipelined loop at N = 2 (7.65 vs 7.39 M rays/s) -
+            but seven ranks pulling the whole slot from ONE source serialise on that GPU (N = 8: 31.5 ms per frame
+            against 5.15 ms with NCCL's pipelined broadcast), so it is opt-in (`transport="ipc"` /
+            ZEST_FRAME_TRANSPORT=ipc) for small worlds.
 Slots are double-buffered and filled on a side stream, so frame k+1 is distributed under the kernels of frame k
 (`prefetch_frame` / `swap_frame`; `set_frame` = both, back to back).  Per target pose every rank renders a contiguous
 slab of the row-major pixel grid; `gather_maps` collects the per-ray maps with ONE all-gather of a packed [rays, 13]
@@ -222,7 +224,11 @@ class FrameRenderer:
             self._tick()                                       # src's pack kernels are finished (stream-ordered on every rank)
             self._mark("side:tickB")
             if self.rank != src:
-                slot.flat.copy_(self._peer_slots(src)[idx], non_blocking=True)    # peer-to-peer pull: copy engines
+                # peer-to-peer pull on THIS device's side stream (copy engines).  Not `Tensor.copy_`: for a cross-device copy
+                # PyTorch switches to the source device and runs the copy on that device's current stream in this process
+                peer = self._peer_slots(src)[idx]
+                _lib.check(_lib.load().zest_memcpy_async(ops._ptr(slot.flat), ops._ptr(peer), slot.flat.numel() * 4, ops._stream()),
+                           "zest_memcpy_async")
             self.transport_used = "ipc"
         else:
             torch.distributed.broadcast(slot.flat, src=src, group=self.group)
