@@ -60,6 +60,10 @@ CASES = {
                          dict(val=False, chain_bwd=True, chain_5frames=True, raw_noise_std=1.0)),
     "train_fwd5": (dict(H=32, W=40, V=3, pad=4, D=32, dynamic=True, seed=8, spread=2.0), 12,
                    dict(val=False, chain_bwd=False, chain_5frames=True, raw_noise_std=0)),
+    # "opaque" variants (alpha bias + 3): a random-init net renders an EMPTY static map (sigma <= 0 everywhere), which
+    # makes rgb / depth comparisons vacuous; these scenes have dense weights on both nets
+    "static_val_opaque": (dict(H=32, W=40, V=3, pad=4, D=32, dynamic=False, seed=9, spread=4.0, opaque=True), 24, dict()),
+    "dynamic_val_opaque": (dict(H=32, W=40, V=3, pad=4, D=32, dynamic=True, seed=10, spread=4.0, opaque=True), 24, dict(val=True)),
 }
 
 

@@ -13,6 +13,8 @@ from tests.helpers import CASES, build_case, load_golden, psnr
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+# bf16 tensor-core render vs the reference's fp32 golden maps: the fp32 bar itself (measured <= 1e-4 on all five scenes)
+BF16_RGB_BAR, BF16_DEPTH_BAR = 2e-3, 2e-3
 
 
 @pytest.fixture(scope="module")
@@ -228,7 +230,7 @@ def _gather_case(zops, name):
     return (x0, y0, z0), pix_cpu, torch.cat([vol_cpu, feats_cpu], -1), feats.cpu(), vox.cpu(), pix.cpu(), R, S
 
 
-@pytest.mark.parametrize("name", ["static_val", "dynamic_val_v10", "train_fwd"])
+@pytest.mark.parametrize("name", ["static_val", "dynamic_val_v10", "train_fwd", "dynamic_val_opaque"])
 def test_gather_indices_bit_exact_and_values(zops, name):
     (x0, y0, z0), pix_cpu, feats_cpu, feats, vox, pix, R, S = _gather_case(zops, name)
     want_vox = torch.stack([x0, y0, z0], -1).reshape(-1, 3).int()
@@ -430,7 +432,8 @@ def _render(zops, name, mode_name, seed_noise=True):
     return got, want, noise
 
 
-@pytest.mark.parametrize("name", ["static_val", "dynamic_val", "dynamic_val_v10", "train_fwd", "train_fwd5"])
+@pytest.mark.parametrize("name", ["static_val", "dynamic_val", "dynamic_val_v10", "train_fwd", "train_fwd5", "static_val_opaque",
+                                  "dynamic_val_opaque"])
 def test_rendering_fp32_matches_reference_golden(zops, name):
     got, want, _ = _render(zops, name, "fp32")
     assert set(got) == set(want), set(got) ^ set(want)
@@ -454,15 +457,14 @@ def test_rendering_train_keys_with_noise(zops):
         assert torch.isfinite(got[k]).all(), k
 
 
-@pytest.mark.parametrize("name", ["static_val", "dynamic_val", "dynamic_val_v10"])
+@pytest.mark.parametrize("name", ["static_val", "dynamic_val", "dynamic_val_v10", "static_val_opaque", "dynamic_val_opaque"])
 def test_rendering_bf16_close_to_reference(zops, name):
     got, want, _ = _render(zops, name, "bf16")
-    for k in ("rgb_map", "rgb_map_ref", "rgb_map_ref_dy"):
-        if k in want:
-            assert float((got[k].cpu() - want[k]).abs().max()) <= 3e-2, k
-    for k in ("depth_map", "depth_map_ref"):
-        if k in want:
-            assert float((got[k].cpu() - want[k]).abs().max()) <= 0.15, k
+    errs = {k: float((got[k].cpu() - want[k]).abs().max()) for k in ("rgb_map", "rgb_map_ref", "rgb_map_ref_dy", "depth_map", "depth_map_ref")
+            if k in want}
+    print(f"   {name} bf16 vs reference golden: " + ", ".join(f"{k} {v:.1e}" for k, v in errs.items()))
+    for k, v in errs.items():
+        assert v <= (BF16_DEPTH_BAR if "depth" in k else BF16_RGB_BAR), (k, v)
 
 
 def test_bf16_psnr_delta_full_frame(zops):
