@@ -945,7 +945,12 @@ def main():
         kw = dict(sc.render_kwargs())
         keys = ("rgb_map", "depth_map") + (("rgb_map_ref", "depth_map_ref", "rgb_map_ref_dy", "depth_map_ref_dy",
                                              "weights_map_dd") if c["dynamic"] else ())
-        host_out = {k: torch.empty((Rl, 3) if "rgb" in k else (Rl,), dtype=torch.float32).pin_memory() for k in keys}
+        # two result sets in pinned host memory: the host waits for frame f - 2's device -> host reads before it reuses a set, so
+        # it never blocks on the frame it has just enqueued (a streaming renderer; every copy still happens inside the timed region)
+        host_outs = [{k: torch.empty((Rl, 3) if "rgb" in k else (Rl,), dtype=torch.float32).pin_memory() for k in keys} for _ in range(2)]
+        host_out = host_outs[0]
+        d2h_done = [None, None]
+        frame_no = {"f": 0}
         copy_stream = torch.cuda.Stream(device=dev)
 
         # two persistent device staging sets (no allocation inside the timed loop: a cudaMalloc there synchronises the device)
@@ -974,6 +979,10 @@ def main():
             return kw
 
         def e2e_step():
+            f = frame_no["f"]; frame_no["f"] += 1
+            if d2h_done[f & 1] is not None:
+                d2h_done[f & 1].synchronize()          # frame f - 2's maps have landed in this result set
+            host_out = host_outs[f & 1]
             job.fr.swap_frame()
             job.prefetch()
             cur = state["next"] or copy_slab(0)
@@ -990,8 +999,8 @@ def main():
                 for k in keys:
                     host_out[k][a:b].copy_(ret[k][0], non_blocking=True)
                 stage_free[i] = torch.cuda.Event(); stage_free[i].record()
+            d2h_done[f & 1] = torch.cuda.Event(); d2h_done[f & 1].record()
             state["next"] = copy_slab(0)          # the next frame's first slab rides under this frame's tail (inside the timed region)
-            torch.cuda.current_stream().synchronize()
 
         for _ in range(2):
             e2e_step()

@@ -1044,7 +1044,7 @@ static int tc_launch(const zest_net* net, TcParams& p, cudaStream_t st) {
   p.tile_counter = nullptr;
   if (!force_static && !ph->cluster2 && net->tc_counters) {
     zest_net* mut = const_cast<zest_net*>(net);
-    p.tile_counter = net->tc_counters + (mut->tc_counter_next++ % kTileCounters);
+    p.tile_counter = net->tc_counters + (mut->tc_counter_next.fetch_add(1, std::memory_order_relaxed) % kTileCounters);
     ZEST_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(int), st));
   }
   int grid = (int)(p.n_tiles < num_sms() ? p.n_tiles : num_sms());

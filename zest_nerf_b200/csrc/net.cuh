@@ -1,5 +1,7 @@
 // Packed parameters of one radiance MLP (networks.py:73-132 Renderer, v0, use_viewdirs).
 #pragma once
+#include <atomic>
+
 #include "common.cuh"
 
 struct zest_net {
@@ -31,7 +33,7 @@ struct zest_net {
   void* tc_plan_host;  // host: layer plan (opaque to everything but mlp_tc.cu)
   void* tc_desc_dev;   // device: pack descriptors (uploaded once)
   int* tc_counters;    // device: ring of tile-scheduler counters (one per launch in flight)
-  unsigned tc_counter_next;
+  std::atomic<unsigned> tc_counter_next;   // host threads launching the same net concurrently must get distinct counters
   bool tc_dirty;       // f32 changed since the bf16 image was built: rebuilt lazily by the next tensor-core launch
 };
 
