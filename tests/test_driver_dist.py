@@ -48,10 +48,22 @@ def _worker(rank, world, port, n_rays):
         maps_small = {"rgb_map": full_rgb[:, s0:s1].clone(), "depth_map": full_d[:, s0:s1].clone()}
         out = fr.gather_maps(maps_small, small, keys=["rgb_map", "depth_map"])
         assert torch.equal(out["rgb_map"], full_rgb[:, :small]) and torch.equal(out["depth_map"], full_d[:, :small])
-        # per-frame broadcast: rank 0 owns the data, the others receive it
-        t = torch.full((4, 5), 7.0) if rank == 0 else torch.zeros((4, 5))
-        dist.broadcast(t, src=0)
-        assert float(t.sum()) == 140.0
+        # per-frame distribution of a packed frame slot: rank 0 owns the data, the others receive every view of it
+        layout = FrameLayout(D=4, Hv=5, Wv=6, V=3, H=8, W=9, NB=4, n_cam=4)
+        fr._ensure_slots(layout)
+        slot = fr._slots[1]
+        if rank == 0:
+            for i, t in enumerate(slot.t.values()):
+                t.copy_(torch.arange(t.numel(), dtype=torch.float32).view(t.shape) + 1000.0 * i)
+        else:
+            slot.flat.zero_()
+        fr._distribute(slot, 1, src=0)
+        assert fr.transport_used == "nccl"          # the collective transport (gloo stands in for NCCL on CPU)
+        for i, (name, t) in enumerate(slot.t.items()):
+            assert torch.equal(t, torch.arange(t.numel(), dtype=torch.float32).view(t.shape) + 1000.0 * i), name
+        frame = slot.frame()
+        assert frame["dynamic"] and frame["V"] == 3 and frame["NB"] == 4 and frame["hw"] == (8, 9)
+        assert frame["vol_d"].shape == (4, 5, 6, 8) and frame["cams_d"].shape == (4, 24)
     finally:
         dist.destroy_process_group()
 
