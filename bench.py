@@ -1023,6 +1023,49 @@ def main():
                "d2h_bytes_per_step": d2h * world, "steps": n_e2e,
                "api": f"{api}, {n_slabs} slabs per rank per frame, pinned host rays, H2D of slab s+1 under the kernels of slab s"}
 
+    # ---------------- e2e through the frame driver: a 4 x 4 target pose in, the maps out ----------------
+    # (the render_spiral / test.py use: rays are built on the device by the bit-exact CUDA ray builder, so a frame's host -> device
+    # traffic is one pose instead of 530 MB of ray tensors; device -> host is the same 52 B / ray of maps)
+    e2e_pose = None
+    if not args.no_e2e:
+        nf2p = torch.stack([sc.near_fars.cpu()[0, 0], sc.near_fars.cpu()[0, -1]]).view(1, 2, 2).to(dev)
+        K_tp = sc.intrinsics[0, -1]
+        pose_host = sc.c2ws.cpu()[0, -1].clone().pin_memory()
+        slab_p = (job.r0, job.r1)
+        host_maps = [None, None]
+        pose_done = [None, None]
+        pf = {"f": 0}
+
+        def pose_step():
+            f = pf["f"]; pf["f"] += 1
+            if pose_done[f & 1] is not None:
+                pose_done[f & 1].synchronize()
+            job.fr.swap_frame()
+            job.prefetch()
+            c2w_d = pose_host.to(dev, non_blocking=True)                       # the step's input: one pose
+            maps = job.fr.render_pose(c2w_d, K_tp, H, W, nf2p, ref_frame_idx=job.t_ref, slab=slab_p)
+            if host_maps[f & 1] is None:
+                host_maps[f & 1] = {k: torch.empty(v.shape, dtype=torch.float32).pin_memory() for k, v in maps.items()}
+            for k, v in maps.items():
+                host_maps[f & 1][k].copy_(v, non_blocking=True)
+            pose_done[f & 1] = torch.cuda.Event(); pose_done[f & 1].record()
+        for _ in range(3):
+            pose_step()
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_p = max(3, args.steps)
+        p0.record()
+        for _ in range(n_p):
+            pose_step()
+        p1.record()
+        barrier()
+        t_p = torch.tensor([p0.elapsed_time(p1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_p, op=dist.ReduceOp.MAX)
+        e2e_pose = {"value": R * n_p / (float(t_p) * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 64 * world,
+                    "d2h_bytes_per_step": sum(v.numel() * 4 for v in host_maps[0].values()) * world, "steps": n_p,
+                    "api": "zest_nerf_b200.driver.FrameRenderer.render_pose (pose in, maps out; CUDA ray builder + fused kernels on the rank's slab)"}
+
     # ---------------- N > 1: the other two multi-GPU figures of the same run ----------------
     pose_parallel = cfg3_strong = None
     if world > 1:
@@ -1147,7 +1190,7 @@ def main():
                 "config": {"workload": args.config + ": " + c["desc"], "rays_per_step": R, "rays_per_gpu_per_step": job.r1 - job.r0, "samples_per_ray": S,
                            "l2": "256 MiB buffer written between timed steps (L2 flush); per-step working set > L2",
                            "parallelism": par},
-                "steps_ms": [round(x, 3) for x in ms], "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 3), "clocks": clocks, "roofline": roofline, "e2e": e2e,
+                "steps_ms": [round(x, 3) for x in ms], "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 3), "clocks": clocks, "roofline": roofline, "e2e": e2e, "e2e_pose_api": e2e_pose,
                 "cpu_baseline": cpu, "parity": parity, "torch_gpu_baseline": tgpu, "sharded_frame_equals_single_gpu": sharded_ok,
                 "pose_parallel_weak": pose_parallel, "cfg3_strong": cfg3_strong,
                 "gather_stage": gstage, "fine_tune": ft, "next_rows": {"f1_ray_builder": f1, "f3_cost_volume": f3, "f3_mvsnet": f3b, "f4_sf_losses": f4, "full_frame_pipeline": pipe}}

@@ -317,8 +317,9 @@ class FrameRenderer:
         fr = self.frame
         r0, r1 = slab if slab is not None else slab_bounds(H * W, self.world, self.rank)
         c2w_tgt, K_tgt = c2w_tgt.to(self.device), K_tgt.to(self.device)
-        w2cs = torch.cat([fr["w2cs"][:, :1], torch.linalg.inv(c2w_tgt.view(1, 1, 4, 4))], 1)
-        c2ws = torch.cat([torch.linalg.inv(fr["w2cs"][:, :1]), c2w_tgt.view(1, 1, 4, 4)], 1)
+        inv = lambda m: torch.linalg.inv_ex(m)[0]          # no error check = no host synchronisation per pose
+        w2cs = torch.cat([fr["w2cs"][:, :1], inv(c2w_tgt.view(1, 1, 4, 4))], 1)
+        c2ws = torch.cat([inv(fr["w2cs"][:, :1]), c2w_tgt.view(1, 1, 4, 4)], 1)
         intr = torch.cat([fr["intrinsics"][:, :1], K_tgt.view(1, 1, 3, 3)], 1)
         outs = []
         for a in range(r0, r1, max_rays):
