@@ -18,6 +18,8 @@
 // memory four channels at a time (cp.async, conflict-free padded rows, two blocks per SM).  It cut conv0's L2 traffic from
 // 22x to 3.5x the input, but its eleven load -> barrier -> compute phases per tile were not hidden by the second block:
 // 1.67 ms against 1.45 ms for the L1-path kernel below.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace zest {
@@ -132,6 +134,22 @@ __global__ void __launch_bounds__(kConvThreads) conv_cl_kernel(const ConvParams 
               const float4* wq = wrow + ((int64_t)kw * p.cin + 4 * q) * 2;
 #pragma unroll
               for (int v = 0; v < kVox; ++v) fma_vox(acc[v], in[v + kw], wq);
+            }
+          }
+        } else if (S == 2 && KW == 3) {
+          // stride 2: 2 VPT + 1 input positions feed VPT outputs x 3 taps (output v reads positions 2 v + kw)
+          for (int q = 0; q < cq; ++q) {
+            float4 in[2 * kVox + 1];
+#pragma unroll
+            for (int i = 0; i < 2 * kVox + 1; ++i) {
+              const int ix = ixb + i;
+              in[i] = (ix >= 0 && ix < p.W) ? __ldg(row + (int64_t)ix * cq + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const float4* wq = wrow + ((int64_t)kw * p.cin + 4 * q) * 2;
+#pragma unroll
+              for (int v = 0; v < kVox; ++v) fma_vox(acc[v], in[2 * v + kw], wq);
             }
           }
         } else {
@@ -332,11 +350,24 @@ int launch_conv_vpt(const ConvParams& p, cudaStream_t st) {
 
 // 8 outputs per thread amortise the weight fetches best, but the coarse levels of the U-Net have too few outputs to fill
 // 148 SMs that way (CostRegNet.conv5: 48 blocks): below ~2 blocks per SM the layer runs with 2 outputs per thread instead.
+// outputs per thread: the largest of 8 / 4 / 2 that still gives ~2 blocks per SM (ZEST_CONV_VPT=8|4|2 forces one: A/B runs)
+static int pick_vpt(int64_t items_w1, int Wo, int cout_tiles, int min_blocks_per_sm = 2) {
+  static const int forced = getenv("ZEST_CONV_VPT") ? atoi(getenv("ZEST_CONV_VPT")) : 0;
+  if (forced == 8 || forced == 4 || forced == 2) return forced;
+  for (int vpt = 8; vpt > 2; vpt >>= 1) {
+    const int64_t blocks = (items_w1 * ((Wo + vpt - 1) / vpt) + kConvThreads - 1) / kConvThreads * cout_tiles;
+    if (blocks >= min_blocks_per_sm * (int64_t)num_sms()) return vpt;
+  }
+  return 2;
+}
+
 template <int KD, int KH, int KW, int S>
 int launch_conv(const ConvParams& p, cudaStream_t st) {
-  const int64_t blocks8 = ((int64_t)p.No * p.Ho * ((p.Wo + 7) / 8) + kConvThreads - 1) / kConvThreads * (p.cout / kCo);
-  if (blocks8 >= 2 * (int64_t)num_sms()) return launch_conv_vpt<KD, KH, KW, S, 8>(p, st);
-  return launch_conv_vpt<KD, KH, KW, S, 2>(p, st);
+  switch (pick_vpt((int64_t)p.No * p.Ho, p.Wo, p.cout / kCo)) {
+    case 8: return launch_conv_vpt<KD, KH, KW, S, 8>(p, st);
+    case 4: return launch_conv_vpt<KD, KH, KW, S, 4>(p, st);
+    default: return launch_conv_vpt<KD, KH, KW, S, 2>(p, st);
+  }
 }
 
 }  // namespace
@@ -393,18 +424,20 @@ extern "C" int zest_convt3_cl_fwd(const float* x, int D, int H, int W, int cin, 
   const size_t smem = (size_t)27 * cin * kCo * sizeof(float);
   ZEST_CHECK_ARG(smem <= 200 * 1024, "zest_convt3_cl_fwd: weight tile does not fit shared memory");
   if (stats) ZEST_CUDA(cudaMemsetAsync(stats, 0, 2 * (size_t)cout * sizeof(double), st));
-  const int64_t blocks8 = ((int64_t)8 * D * H * ((W + 7) / 8) + kConvThreads - 1) / kConvThreads * (cout / kCo);
-  if (blocks8 >= 2 * (int64_t)num_sms()) {
-    ZEST_CUDA(cudaFuncSetAttribute(convt3_cl_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t items = (int64_t)8 * D * H * ((W + 7) / 8);
-    dim3 grid((unsigned)((items + kConvThreads - 1) / kConvThreads), (unsigned)(cout / kCo));
-    convt3_cl_kernel<8><<<grid, kConvThreads, smem, st>>>(p);
-  } else {
-    ZEST_CUDA(cudaFuncSetAttribute(convt3_cl_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t items = (int64_t)8 * D * H * ((W + 1) / 2);
-    dim3 grid((unsigned)((items + kConvThreads - 1) / kConvThreads), (unsigned)(cout / kCo));
-    convt3_cl_kernel<2><<<grid, kConvThreads, smem, st>>>(p);
+#define ZEST_CONVT(VPT)                                                                                              \
+  do {                                                                                                             \
+    ZEST_CUDA(cudaFuncSetAttribute(convt3_cl_kernel<VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    const int64_t items = (int64_t)8 * D * H * ((W + VPT - 1) / VPT);                                              \
+    dim3 grid((unsigned)((items + kConvThreads - 1) / kConvThreads), (unsigned)(cout / kCo));                      \
+    convt3_cl_kernel<VPT><<<grid, kConvThreads, smem, st>>>(p);                                                    \
+  } while (0)
+  // the transposed convolutions have 1 - 8 taps per output and little reuse to lose: they prefer more, smaller threads
+  switch (pick_vpt((int64_t)8 * D * H, W, cout / kCo, 8)) {
+    case 8: ZEST_CONVT(8); break;
+    case 4: ZEST_CONVT(4); break;
+    default: ZEST_CONVT(2); break;
   }
+#undef ZEST_CONVT
   ZEST_LAUNCH_CHECK();
   return ZEST_OK;
 }
