@@ -17,7 +17,10 @@
 // Tried and removed (round 2, same-box A/B): staging the 3 x 18 x 66 input halo of a 16 x 64 output tile through shared
 // memory four channels at a time (cp.async, conflict-free padded rows, two blocks per SM).  It cut conv0's L2 traffic from
 // 22x to 3.5x the input, but its eleven load -> barrier -> compute phases per tile were not hidden by the second block:
-// 1.67 ms against 1.45 ms for the L1-path kernel below.
+// 1.67 ms against 1.45 ms for the L1-path kernel below.  Also tried and removed: the cost volume as planes of channel quads with
+// the lanes of a warp on consecutive voxels (every load 512 contiguous bytes = 4 cache lines instead of 32: ncu shows conv0
+// bound by L1 tag lookups, 31 sectors per request, 13 % L1 hit rate) - without the sliding register window it needs 2.4x the
+// load instructions and came out at 1.80 ms.
 #include <cstdlib>
 
 #include "common.cuh"
