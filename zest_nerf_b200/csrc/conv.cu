@@ -20,7 +20,9 @@
 // 1.67 ms against 1.45 ms for the L1-path kernel below.  Also tried and removed: the cost volume as planes of channel quads with
 // the lanes of a warp on consecutive voxels (every load 512 contiguous bytes = 4 cache lines instead of 32: ncu shows conv0
 // bound by L1 tag lookups, 31 sectors per request, 13 % L1 hit rate) - without the sliding register window it needs 2.4x the
-// load instructions and came out at 1.80 ms.
+// load instructions and came out at 1.80 ms.  And: 256-bit loads (LDG.E.256, 8 channels per request, 48-channel records) in the
+// sliding window - conv0 alone 1.32 ms under ncu, but 255 registers per thread and a 9 % fatter cost volume made the whole forward
+// slower in the graph replay (4.0 vs 3.6 ms).
 #include <cstdlib>
 
 #include "common.cuh"
