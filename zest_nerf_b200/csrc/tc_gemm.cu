@@ -35,6 +35,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cuda.h>   // CUtensorMap and the cuTensorMapEncodeTiled prototype only: the entry point is looked up through the runtime
+
 #include "sgemm.cuh"
 #include "tc_ptx.cuh"
 
@@ -65,6 +67,9 @@ __device__ __forceinline__ void gemm_wait(uint32_t bar, uint32_t parity, int tag
   }
 }
 
+#ifndef ZEST_TF32_SPLIT
+#define ZEST_TF32_SPLIT 0   // 0: cvt.rna head and residual; 1 / 2: integer-rounded head, masked / raw residual (same measured error and time)
+#endif
 __device__ __forceinline__ uint32_t to_tf32(float a) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
@@ -98,8 +103,16 @@ __device__ __forceinline__ void split_chunk(const float* v, uint32_t (&h)[4], ui
   } else {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
+#if ZEST_TF32_SPLIT == 0
       h[e] = to_tf32(v[e]);
       l[e] = to_tf32(v[e] - __uint_as_float(h[e]));
+#else
+      h[e] = (__float_as_uint(v[e]) + 0x1000u) & 0xffffe000u;
+      l[e] = __float_as_uint(v[e] - __uint_as_float(h[e]));
+#if ZEST_TF32_SPLIT == 1
+      l[e] &= 0xffffe000u;
+#endif
+#endif
     }
   }
 }
@@ -523,24 +536,76 @@ __global__ void gemm_pack_b_kernel(const float* __restrict__ B, int64_t sb_j, in
 
 constexpr int kWorkers = 256;              // warps 0..7 stage A and run the epilogue; warp 8 drives the TMA and the UMMAs
 
+#ifdef ZEST_GEMM_TIMELINE     // developer build: clock64 stamps of CTAs 1000..1007 of the packed kernel (tools/gemm_timeline.py)
+__device__ unsigned long long g_gemm_tl[8 * 128];
+#define GTL(slot, cond) do { if (blockIdx.x >= 1000 && blockIdx.x < 1008 && (cond)) g_gemm_tl[(blockIdx.x - 1000) * 128 + (slot)] = clock64(); } while (0)
+#else
+#define GTL(slot, cond) do { } while (0)
+#endif
+
 // DUAL = false: 128 x 256 tile, one accumulator (256 TMEM columns), 2 stages of 48 KB.
 // DUAL = true:  128 x 128 tile; the head product a_hi*b_hi accumulates in TMEM columns [0,128), the two cross products in
 //               [128,256), added in the epilogue in fp32; 3 stages of 32 KB.  The tensor core's fp32 accumulate truncates,
 //               a bias that compounds layer by layer through the MLP's forward / dX chain; the main accumulator now sees a
 //               third of the UMMAs and the cross accumulator is 2^-11 of its magnitude.
 // Either way 96 KB of shared memory and 256 TMEM columns: two CTAs per SM, one's epilogue under the other's main loop.
-template <int KCH, bool AKC, bool DUAL>
-__global__ void __launch_bounds__(kWorkers + 32, 2) tc_gemm_packed_kernel(GemmArgs g, const uint8_t* __restrict__ bpack) {
+// Ring geometry of the packed kernel.  Three rings, sized separately:
+//   A ring    NSA slots of hi + lo images (16 KB), written by the workers, read by the UMMAs
+//   B ring    NSB slots of packed weights (16 / 32 KB), bulk copies out of L2 issued NSB - 1 stages ahead by the issue warp
+//   landing   NR slots of one fp32 A stage (8 KB) as a 2-D tensor copy lands it (TMA_A launches): a tenth warp streams the row
+//             tile NR stages ahead; the workers read LDS -> split -> STS.  Without it (operand not k-contiguous / not 16-byte
+//             aligned) the workers stage A through registers, up to 6 stages ahead.
+// Measured on the forward layer GEMM [524288,256] x [256,256], engine 2 (tools/gemm_timeline.py, stamps per stage): with
+// register staging a stage took ~2200 cycles while the loads of stage + 6 were being issued and ~1000 without - the LSU path
+// (8 half-lines per LDG.128, 2 CTAs x 96 KB in flight) was the bound, not HBM (39 %), the tensor pipe (26 %) or the ALU split
+// (a 3x cheaper split changed nothing).  Tensor copies take the loads off the LSU: 0.615 -> 0.440 ms.
+// The ring split 2 A + 4 B (vs 3 + 3) was worth 2 %; 112 KB rings lose the second CTA and are slower.
+#ifndef ZEST_GEMM_NSA_DUAL
+#define ZEST_GEMM_NSA_DUAL 2
+#endif
+#ifndef ZEST_GEMM_NSB_DUAL
+#define ZEST_GEMM_NSB_DUAL 4
+#endif
+template <bool DUAL, bool TMA_A>
+struct PackedRing {
+  static constexpr int TN = DUAL ? 128 : 256;                // output columns per CTA
+  static constexpr uint32_t kBH = TN * 64;                   // bytes of one part (hi or lo) of a B stage
+  static constexpr uint32_t kABytes = 2 * kAHalf, kBBytes = 2 * kBH;
+  static constexpr uint32_t kRawBytes = GM * 64;             // one fp32 stage of A as the tensor copy lands it: 128 rows x 64 B
+  static constexpr int NSA = DUAL ? ZEST_GEMM_NSA_DUAL : 2;
+  static constexpr int NSB = DUAL ? (TMA_A ? 3 : ZEST_GEMM_NSB_DUAL) : 2;
+  static constexpr int NR = TMA_A ? 4 : 0;                   // fp32 landing slots of the A tensor copies
+  static constexpr uint32_t kBRing = NSA * kABytes, kRawRing = kBRing + NSB * kBBytes;
+  static constexpr uint32_t kBytes = kRawRing + NR * kRawBytes;
+  static constexpr uint32_t kTail = 256;                     // barriers + TMEM base behind the rings
+  static constexpr int gcd(int a, int b) { return b == 0 ? a : gcd(b, a % b); }
+  static constexpr int U = NSA * NSB / gcd(NSA, NSB);        // the issue loop is unrolled by this: slot numbers are immediates
+  static_assert(kBytes + kTail + 1024 <= 233472 / 2, "two CTAs per SM (228 KB, 1 KB reserved per CTA)");
+  static_assert(8 * 32 * kEpiRow <= kRawRing, "epilogue staging must fit in the A and B rings");
+};
+
+template <int KCH, bool AKC, bool DUAL, bool TMA_A>
+__global__ void __launch_bounds__(kWorkers + 64, 2) tc_gemm_packed_kernel(GemmArgs g, const uint8_t* __restrict__ bpack,
+                                                                          const __grid_constant__ CUtensorMap amap) {
+  static_assert(!TMA_A || (AKC && KCH == 4), "the A tensor copies land fp32 stages of 16 k");
+  using Ring = PackedRing<DUAL, TMA_A>;
   constexpr int GK = 4 * KCH;
-  constexpr int TN = DUAL ? 128 : 256;                      // output columns per CTA
-  constexpr uint32_t kBH = TN * 64;                         // bytes of one part (hi or lo) of the B stage
-  constexpr uint32_t kStg = 2 * kAHalf + 2 * kBH;
-  constexpr int NS = DUAL ? 3 : 2;                          // smem stages
-  constexpr int PD = NS - 1;                                // the TMA runs this many stages ahead of the UMMAs
-  static_assert(NS * kStg <= kSmem, "stages must fit in 96 KB");
+  constexpr int TN = Ring::TN;
+  constexpr uint32_t kBH = Ring::kBH;
+  constexpr int NSA = Ring::NSA, NSB = Ring::NSB, U = Ring::U;
+  constexpr int PD = NSB - 1;                               // the weight copies run this many stages ahead of the UMMAs
+  constexpr uint32_t kBRing = Ring::kBRing;                 // byte offset of the B ring
+  constexpr int NR = TMA_A ? Ring::NR : 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t empty_bar[NS], full_bar[NS], aready_bar[NS];
-  __shared__ uint32_t s_tmem;
+  // barriers and the TMEM base live behind the rings in the dynamic allocation (a static __shared__ block next to a
+  // 1024-byte-aligned extern array costs 2 KB of padding, which is what decides whether two CTAs fit)
+  uint64_t* const empty_bar = reinterpret_cast<uint64_t*>(smem_raw + Ring::kBytes);
+  uint64_t* const full_bar = empty_bar + NSA;
+  uint64_t* const aready_bar = full_bar + NSB;
+  uint64_t* const raw_full = aready_bar + NSA;
+  uint64_t* const raw_empty = raw_full + NR;
+  uint32_t& s_tmem = *reinterpret_cast<uint32_t*>(raw_empty + NR);
+  static_assert((2 * NSA + NSB + 2 * NR + 1) * 8 <= (int)Ring::kTail, "barrier block");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // column tiles of one row tile are adjacent CTAs: the second reader of an A tile hits L2
   const int tiles_n = (g.J + TN - 1) / TN;
@@ -553,12 +618,19 @@ __global__ void __launch_bounds__(kWorkers + 32, 2) tc_gemm_packed_kernel(GemmAr
   const int nkt = (int)((g.K + GK - 1) / GK);
 
   const uint32_t smem0 = ptx::smem_u32(smem_raw);
+  GTL(0, tid == 0);
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
+    for (int s = 0; s < NSA; ++s) {
       ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&aready_bar[s]), kWorkers / 32);
+    }
+#pragma unroll
+    for (int s = 0; s < NSB; ++s) ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
+#pragma unroll
+    for (int s = 0; s < NR; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&raw_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&raw_empty[s]), kWorkers / 32);
     }
     ptx::fence_mbar_init();
   }
@@ -567,22 +639,22 @@ __global__ void __launch_bounds__(kWorkers + 32, 2) tc_gemm_packed_kernel(GemmAr
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = s_tmem;
+  GTL(1, tid == 0);
 
   if (warp == 8) {
     // The issue warp stays converged: every lane polls the barriers, one elected lane issues.  Slot numbers are compile-time
-    // (the stage loop is unrolled by NS), so every descriptor is a warp-uniform base plus an immediate - no per-UMMA
-    // register-to-uniform waterfall (measured ~90 cycles per UMMA in the MLP kernel) on the issue path.
+    // (the stage loop is unrolled by U = lcm(NSA, NSB)), so every descriptor is a warp-uniform base plus an immediate - no
+    // per-UMMA register-to-uniform waterfall (measured ~90 cycles per UMMA in the MLP kernel) on the issue path.
     const uint8_t* src = bpack + (size_t)bn * nkt * (2 * kBH);
     const uint32_t idesc = KCH == 8 ? ptx::idesc_bf16(n_mma) : idesc_tf32(n_mma);
     constexpr uint64_t kHi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;                    // SBO = 128 B, descriptor version 1
     constexpr uint32_t kALbo = ((uint32_t)(GM * 16) >> 4) << 16, kBLbo = ((uint32_t)(TN * 16) >> 4) << 16;
     const uint32_t lo0 = (smem0 >> 4) & 0x3FFFu;
     const uint32_t cross = DUAL ? tmem + TN : tmem;
-    auto load_b = [&](int t, int slot_i) {   // weights of stage t -> slot t % NS (= slot_i)
-      const uint32_t slot = smem0 + (uint32_t)slot_i * kStg;
+    auto load_b = [&](int t, int slot_i) {   // weights of stage t -> B slot t % NSB (= slot_i)
       const uint32_t bar = ptx::smem_u32(&full_bar[slot_i]);
       ptx::mbar_arrive_expect_tx(bar, 2 * kBH);
-      ptx::bulk_g2s(slot + 2 * kAHalf, src + (size_t)t * (2 * kBH), 2 * kBH, bar);
+      ptx::bulk_g2s(smem0 + kBRing + (uint32_t)slot_i * Ring::kBBytes, src + (size_t)t * (2 * kBH), 2 * kBH, bar);
     };
     if (ptx::elect_one()) {
 #pragma unroll
@@ -590,23 +662,26 @@ __global__ void __launch_bounds__(kWorkers + 32, 2) tc_gemm_packed_kernel(GemmAr
         if (t < nkt) load_b(t, t);
     }
     __syncwarp();
-    uint32_t par = 0;
-    for (int kt0 = 0; kt0 < nkt; kt0 += NS, par ^= 1u) {
+    for (int kt0 = 0; kt0 < nkt; kt0 += U) {
 #pragma unroll
-      for (int u = 0; u < NS; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int kt = kt0 + u;
         if (kt >= nkt) break;
-        gemm_wait(ptx::smem_u32(&aready_bar[u]), par, 4);
-        gemm_wait(ptx::smem_u32(&full_bar[u]), par, 5);
+        const int sa = u % NSA, sb = u % NSB;               // kt0 is a multiple of both ring sizes
+        gemm_wait(ptx::smem_u32(&aready_bar[sa]), (uint32_t)(kt / NSA) & 1u, 4);
+        gemm_wait(ptx::smem_u32(&full_bar[sb]), (uint32_t)(kt / NSB) & 1u, 5);
         ptx::tc_fence_after();
+        GTL(kt == 0 ? 6 : 7, lane == 0);      // first stage ready / every later stage ready (the last write = the last stage)
+        GTL(16 + kt * 4 + 3, lane == 0 && kt < 24);
         if (ptx::elect_one()) {
-          const uint32_t slot_lo = lo0 + (uint32_t)u * (kStg >> 4);
+          const uint32_t a_slot = lo0 + (uint32_t)sa * (Ring::kABytes >> 4);
+          const uint32_t b_slot = lo0 + (kBRing >> 4) + (uint32_t)sb * (Ring::kBBytes >> 4);
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t a_hi = kHi | (uint64_t)((slot_lo + ks * ((2 * GM * 16) >> 4)) | kALbo);
-            const uint64_t a_lo = kHi | (uint64_t)((slot_lo + (kAHalf >> 4) + ks * ((2 * GM * 16) >> 4)) | kALbo);
-            const uint64_t b_hi = kHi | (uint64_t)((slot_lo + ((2 * kAHalf) >> 4) + ks * ((2 * TN * 16) >> 4)) | kBLbo);
-            const uint64_t b_lo = kHi | (uint64_t)((slot_lo + ((2 * kAHalf + kBH) >> 4) + ks * ((2 * TN * 16) >> 4)) | kBLbo);
+            const uint64_t a_hi = kHi | (uint64_t)((a_slot + ks * ((2 * GM * 16) >> 4)) | kALbo);
+            const uint64_t a_lo = kHi | (uint64_t)((a_slot + (kAHalf >> 4) + ks * ((2 * GM * 16) >> 4)) | kALbo);
+            const uint64_t b_hi = kHi | (uint64_t)((b_slot + ks * ((2 * TN * 16) >> 4)) | kBLbo);
+            const uint64_t b_lo = kHi | (uint64_t)((b_slot + (kBH >> 4) + ks * ((2 * TN * 16) >> 4)) | kBLbo);
             const uint32_t acc0 = (kt > 0 || ks > 0) ? 1u : 0u;
             if constexpr (KCH == 8) {
               ptx::mma_bf16_ss(cross, a_lo, b_hi, idesc, acc0);
@@ -618,17 +693,76 @@ __global__ void __launch_bounds__(kWorkers + 32, 2) tc_gemm_packed_kernel(GemmAr
               mma_tf32_ss(tmem, a_hi, b_hi, idesc, DUAL ? acc0 : 1u);
             }
           }
-          ptx::mma_commit(ptx::smem_u32(&empty_bar[u]));
+          ptx::mma_commit(ptx::smem_u32(&empty_bar[sa]));   // frees the A slot for the workers and (below) the B slot
         }
         __syncwarp();
-        if (kt + PD < nkt) {   // stage kt + PD reuses the slot of stage kt - 1: free once those UMMAs have retired
-          const int pu = (u + NS - 1) % NS;
-          if (kt >= 1) gemm_wait(ptx::smem_u32(&empty_bar[pu]), u == 0 ? (par ^ 1u) : par, 3);
-          if (ptx::elect_one()) load_b(kt + PD, pu);
+        if (kt + PD < nkt) {   // stage kt + PD reuses the B slot of stage kt - 1: free once those UMMAs have retired
+          const int pa = (u + U - 1) % NSA, pb = (u + U - 1) % NSB;
+          if (kt >= 1) gemm_wait(ptx::smem_u32(&empty_bar[pa]), (uint32_t)((kt - 1) / NSA) & 1u, 3);
+          if (ptx::elect_one()) load_b(kt + PD, pb);
           __syncwarp();
         }
       }
     }
+  } else if (warp == 9) {
+    // A producer (TMA_A launches only): one lane streams the row tile's fp32 stages into the landing ring, NR - 1 ahead of
+    // the workers.  Rows past I and columns past K arrive as zeros (the map's bounds), the box always counts 8 KB.
+    if constexpr (TMA_A) {
+      if (lane == 0) {
+        ptx::prefetch_tensormap(&amap);
+        for (int kt = 0; kt < nkt; ++kt) {
+          const int rs = kt % NR;
+          if (kt >= NR) gemm_wait(ptx::smem_u32(&raw_empty[rs]), (uint32_t)(kt / NR - 1) & 1u, 7);
+          const uint32_t bar = ptx::smem_u32(&raw_full[rs]);
+          ptx::mbar_arrive_expect_tx(bar, Ring::kRawBytes);
+          ptx::tma_load_2d(smem0 + Ring::kRawRing + (uint32_t)rs * Ring::kRawBytes, &amap, kt * GK, (int)i0, bar);
+        }
+      }
+    }
+  } else if constexpr (TMA_A) {
+    // workers: fp32 stage out of the landing ring (64-byte rows, 16-byte chunks XOR-swizzled by the copy: chunk ^ (row / 2) % 4,
+    // which makes the 8 rows a quarter-warp reads hit 8 distinct bank groups) -> hi / lo images of the A slot
+    GTL(2, tid == 0);
+    for (int kt = 0; kt < nkt; ++kt) {
+      const int rs = kt % NR, sa = kt % NSA;
+      const uint32_t raw = smem0 + Ring::kRawRing + (uint32_t)rs * Ring::kRawBytes;
+      const uint32_t slot = smem0 + (uint32_t)sa * Ring::kABytes;
+      gemm_wait(ptx::smem_u32(&raw_full[rs]), (uint32_t)(kt / NR) & 1u, 6);
+      uint4 w[2];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const int u = tid + n * kThreads;
+        const int row = (u >> 5) * 8 + (u & 7), c = (u >> 3) & 3;
+        w[n] = ptx::ld_smem_v4(raw + (uint32_t)row * 64 + (uint32_t)((c ^ ((row >> 1) & 3)) << 4));
+      }
+      if (kt >= NSA) gemm_wait(ptx::smem_u32(&empty_bar[sa]), (uint32_t)(kt / NSA - 1) & 1u, 1);
+      GTL(16 + kt * 4 + 0, tid == 0 && kt < 24);
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const int u = tid + n * kThreads;
+        const int row = (u >> 5) * 8 + (u & 7), c = (u >> 3) & 3;
+        const float v[4] = {__uint_as_float(w[n].x), __uint_as_float(w[n].y), __uint_as_float(w[n].z), __uint_as_float(w[n].w)};
+        const uint32_t off = (uint32_t)c * (GM * 16) + (uint32_t)row * 16;
+        store_chunk<KCH>(slot + off, slot + kAHalf + off, v);
+      }
+      GTL(16 + kt * 4 + 1, tid == 0 && kt < 24);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(ptx::smem_u32(&aready_bar[sa]));
+        // The landing slot is released only now, behind the stores that consumed its values.  Releasing it right after
+        // the LDS was a measured bug: the UMMAs' operand reads can hold the shared-memory pipe long enough for the LDS to
+        // execute after the refill of the slot had started (rows of stage kt + NR in the image of stage kt).
+        ptx::mbar_arrive(ptx::smem_u32(&raw_empty[rs]));
+      }
+      GTL(16 + kt * 4 + 2, tid == 0 && kt < 24);
+    }
+    GTL(3, tid == 0);
+    gemm_wait(ptx::smem_u32(&empty_bar[(nkt - 1) % NSA]), (uint32_t)((nkt - 1) / NSA) & 1u, 2);
+    ptx::tc_fence_after();
+    GTL(4, tid == 0);
+    gemm_epilogue<DUAL ? TN : 0>(g, tmem, smem0, warp, lane, i0, j0, im, jn, n_mma, false, true);
+    GTL(5, tid == 0);
   } else {
     // workers: A NSET stages ahead in registers (static register sets), no CTA-wide barrier in the loop
     constexpr int NSET = KCH == 4 ? 6 : 2;     // a tf32 stage is 8 registers per thread, a bf16 stage 16
@@ -638,34 +772,72 @@ __global__ void __launch_bounds__(kWorkers + 32, 2) tc_gemm_packed_kernel(GemmAr
     for (int u = 0; u < NSET; ++u)
       if (u < nkt) rs[u].fetch(g.A, a_s, g.I, i0, (int64_t)u * GK, g.K, GM, tid);
     auto step = [&](auto& r, int kt) {
-      const int s = kt % NS;
-      const uint32_t slot = smem0 + (uint32_t)s * kStg;
-      if (kt >= NS) gemm_wait(ptx::smem_u32(&empty_bar[s]), (uint32_t)(kt / NS - 1) & 1u, 1);
+      const int s = kt % NSA;
+      const uint32_t slot = smem0 + (uint32_t)s * Ring::kABytes;
+      if (kt >= NSA) gemm_wait(ptx::smem_u32(&empty_bar[s]), (uint32_t)(kt / NSA - 1) & 1u, 1);
+      GTL(16 + kt * 4 + 0, tid == 0 && kt < 24);
       r.store(slot, slot + kAHalf, GM, tid);
       if (kt + NSET < nkt) r.fetch(g.A, a_s, g.I, i0, (int64_t)(kt + NSET) * GK, g.K, GM, tid);
+      GTL(16 + kt * 4 + 1, tid == 0 && kt < 24);
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&aready_bar[s]));
+      GTL(16 + kt * 4 + 2, tid == 0 && kt < 24);
     };
+    GTL(2, tid == 0);
     for (int kt = 0; kt < nkt; kt += NSET) {
 #pragma unroll
       for (int u = 0; u < NSET; ++u)
         if (kt + u < nkt) step(rs[u], kt + u);
     }
-    gemm_wait(ptx::smem_u32(&empty_bar[(nkt - 1) % NS]), (uint32_t)((nkt - 1) / NS) & 1u, 2);
+    GTL(3, tid == 0);
+    gemm_wait(ptx::smem_u32(&empty_bar[(nkt - 1) % NSA]), (uint32_t)((nkt - 1) / NSA) & 1u, 2);
     ptx::tc_fence_after();
+    GTL(4, tid == 0);
     gemm_epilogue<DUAL ? TN : 0>(g, tmem, smem0, warp, lane, i0, j0, im, jn, n_mma, false, true);
+    GTL(5, tid == 0);
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 8) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 256); }
+  GTL(8, tid == 0);
 }
 
-template <int KCH, bool AKC, bool DUAL>
-int launch_packed_variant(const GemmArgs& a, dim3 grid, cudaStream_t st) {
+// A tensor map over a k-contiguous fp32 A[I, K] (row stride lda floats): boxes of 16 k x 128 rows, 64-byte swizzle.
+// False when the operand does not qualify (alignment) or the driver entry point is missing: the caller keeps the register path.
+using TensorMapEncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeFn tensor_map_encoder() {
+  static const TensorMapEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<TensorMapEncodeFn>(p);
+  }();
+  return fn;
+}
+bool encode_a_map(const GemmArgs& a, CUtensorMap* map) {
+  if (std::getenv("ZEST_GEMM_NO_TMA_A")) return false;           // developer A/B switch
+  if (a.sa_k != 1 || (reinterpret_cast<uintptr_t>(a.A) & 15) != 0 || (a.sa_i & 3) != 0 || a.sa_i < a.K) return false;
+  if (a.I >= (1ll << 31) || a.K >= (1ll << 31) || a.sa_i * 4 >= (1ll << 40)) return false;
+  const TensorMapEncodeFn enc = tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.I};
+  const cuuint64_t strides[1] = {(cuuint64_t)a.sa_i * 4};
+  const cuuint32_t box[2] = {16, (cuuint32_t)GM};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.A), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int KCH, bool AKC, bool DUAL, bool TMA_A>
+int launch_packed_variant(const GemmArgs& a, dim3 grid, const CUtensorMap& amap, cudaStream_t st) {
   // the attribute is per device: set it on every launch (a few hundred ns) rather than once per process
-  ZEST_CUDA(cudaFuncSetAttribute(tc_gemm_packed_kernel<KCH, AKC, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
-  tc_gemm_packed_kernel<KCH, AKC, DUAL><<<grid, kWorkers + 32, kSmem, st>>>(a, (const uint8_t*)a.b_scratch);
+  constexpr int kBytes = (int)(PackedRing<DUAL, TMA_A>::kBytes + PackedRing<DUAL, TMA_A>::kTail);
+  ZEST_CUDA(cudaFuncSetAttribute(tc_gemm_packed_kernel<KCH, AKC, DUAL, TMA_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes));
+  tc_gemm_packed_kernel<KCH, AKC, DUAL, TMA_A><<<grid, kWorkers + (TMA_A ? 64 : 32), kBytes, st>>>(a, (const uint8_t*)a.b_scratch, amap);
   ZEST_LAUNCH_CHECK();
   return ZEST_OK;
 }
@@ -687,7 +859,13 @@ int launch_packed(const GemmArgs& a, cudaStream_t st) {
   const int64_t total = tiles_n * nst * 4 * TN;
   gemm_pack_b_kernel<KCH, TN><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a.B, a.sb_j, a.sb_k, a.J, a.K, nst, total, (uint8_t*)a.b_scratch);
   ZEST_LAUNCH_CHECK();
-  return a.sa_k == 1 ? launch_packed_variant<KCH, true, DUAL>(a, grid, st) : launch_packed_variant<KCH, false, DUAL>(a, grid, st);
+  CUtensorMap amap;
+  std::memset(&amap, 0, sizeof(amap));
+  if constexpr (KCH == 4) {   // k-contiguous fp32 activations: tensor copies feed the A stages, no loads through the LSU
+    if (encode_a_map(a, &amap)) return launch_packed_variant<KCH, true, DUAL, true>(a, grid, amap, st);
+  }
+  return a.sa_k == 1 ? launch_packed_variant<KCH, true, DUAL, false>(a, grid, amap, st)
+                     : launch_packed_variant<KCH, false, DUAL, false>(a, grid, amap, st);
 }
 
 template <int KCH, bool AKC, bool BKC>
@@ -766,6 +944,14 @@ int launch_gemm_tc(const GemmArgs& a0, int engine, cudaStream_t st) {
 }  // namespace zest
 
 using namespace zest;
+
+#ifdef ZEST_GEMM_TIMELINE
+extern "C" int zest_gemm_read_timeline(unsigned long long* host_out) {
+  ZEST_CUDA(cudaDeviceSynchronize());
+  ZEST_CUDA(cudaMemcpyFromSymbol(host_out, g_gemm_tl, sizeof(unsigned long long) * 8 * 128));
+  return ZEST_OK;
+}
+#endif
 
 extern "C" int zest_set_gemm_engine(int engine) {
   const int prev = gemm_engine();
