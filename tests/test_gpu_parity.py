@@ -125,6 +125,26 @@ def test_tc_gemm_matches_fp32(zops, lib, I, J, K, a_kc, b_kc):
     assert e_bf16 <= 3e-5, f"3 x bf16 GEMM error {e_bf16:.2e} (SIMT fp32: {e_simt:.2e})"
 
 
+@pytest.mark.parametrize("I,K,lda", [(2048, 256, 256), (2085, 256, 256), (1536, 320, 320), (1100, 319, 320)])
+def test_tc_gemm_identity_exact(zops, lib, I, K, lda):
+    """C = A x Identity^T on the default engine must return A bit for bit (integers are exact in hi + lo): every element is its
+    own witness of which (row, k) of A the kernel staged.  Regression test of the tensor-copy-fed A path (tc_gemm.cu): a landing
+    slot released before its loads had executed showed up here as rows of stage kt + 4 in the image of stage kt; the strided
+    case (row stride 320 > K = 319) covers the zero fill past K."""
+    A = torch.zeros((I, lda))
+    A[:, :K] = (torch.arange(I * K, dtype=torch.float32).reshape(I, K) % 65536) + 1.0
+    Bm = torch.eye(K)
+    Ad, Bd = A.to(DEV), Bm.to(DEV)
+    if lda > K:
+        Ad[:, K:] = float("nan")          # padding columns must never reach the product
+    scratch = torch.empty((2 << 20,), dtype=torch.uint8, device=DEV)
+    for rep in range(3):                  # the bug was a race: a few launches
+        Cm = torch.full((I, K), -1.0, device=DEV)
+        _gemm(lib, Ad, (lda, 1), Bd, (K, 1), Cm, I, K, K, engine=2, scratch=scratch)
+        bad = int((Cm.cpu() != A[:, :K]).sum())
+        assert bad == 0, f"{bad} elements of A staged wrong (rep {rep})"
+
+
 @pytest.mark.parametrize("engine", [1, 2])
 def test_tc_gemm_writes_only_its_output(zops, lib, engine):
     """Guard bands instead of compute-sanitizer (closed on this pool): C lives inside a larger sentinel-filled buffer with a

@@ -513,6 +513,167 @@ __global__ void __launch_bounds__(kThreads, 2) tc_gemm_kernel(GemmArgs g, int64_
   if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 256); }
 }
 
+// ---- both operands row-contiguous activations, long K (dW = dZ^T H over 524 288 samples): tensor-copy-fed variant.
+// One CTA per SM owns a 256 x 256 output tile (two 128-row accumulators = all 512 TMEM columns, so both halves share one
+// staging of the B operand) and one K slice.  A producer lane lands fp32 steps of 16 k x 256 features of A and of B
+// (2 x 16 KB, plain [k][feature] rows: features past I / J and samples past K arrive as zeros) in a 4-slot ring; 16 worker
+// warps read their (row, 8-k chunk) with eight conflict-free 4-byte shared loads - the transposition into the K-major
+// images is that read pattern, no global load touches the LSU -, split to bf16 head + residual and store 16-byte chunks
+// into a 3-slot image ring; the issue warp runs 6 UMMAs (2 row halves x 3 products, N = 256, K = 16) per step.
+// Measured before it (tools/gemm_bench.py dW, register-staged kernel, 0.31 ms): without the UMMAs 0.30, without the loads
+// 0.15, without either 0.12 - the exposed load latency of a one-stage register prefetch was half the kernel.
+constexpr int kRcWorkers = 512;
+struct RcRing {
+  static constexpr int RM = 256;                               // rows of A (and of B) per CTA
+  static constexpr int SK = 16;                                // k per step = one bf16 UMMA
+  static constexpr uint32_t kRawOp = SK * RM * 4;              // one operand's fp32 step: 16 KB
+  static constexpr uint32_t kRawBytes = 2 * kRawOp;            // A then B
+  static constexpr uint32_t kPart = 2 * RM * 16;               // hi or lo image of one operand: 2 chunks x 256 rows x 16 B = 8 KB
+  static constexpr uint32_t kImgBytes = 4 * kPart;             // A_hi | A_lo | B_hi | B_lo
+  static constexpr int NI = 3, NR = 4;
+  static constexpr uint32_t kRawRing = NI * kImgBytes;
+  static constexpr uint32_t kBytes = kRawRing + NR * kRawBytes;
+  static constexpr uint32_t kTail = 256;
+  static_assert(kBytes + kTail <= 232448, "one CTA per SM: 227 KB");
+  static_assert(16 * 32 * kEpiRow <= kRawRing, "epilogue staging of 16 warps must fit in the image ring");
+};
+
+__global__ void __launch_bounds__(kRcWorkers + 64, 1) tc_gemm_rc_tma_kernel(GemmArgs g, int64_t kper,
+                                                                           const __grid_constant__ CUtensorMap amap,
+                                                                           const __grid_constant__ CUtensorMap bmap) {
+  using R = RcRing;
+  constexpr int NI = R::NI, NR = R::NR;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint64_t* const img_empty = reinterpret_cast<uint64_t*>(smem_raw + R::kBytes);
+  uint64_t* const img_ready = img_empty + NI;
+  uint64_t* const raw_full = img_ready + NI;
+  uint64_t* const raw_empty = raw_full + NR;
+  uint32_t& s_tmem = *reinterpret_cast<uint32_t*>(raw_empty + NR);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t i0 = (int64_t)blockIdx.x * R::RM;
+  const int j0 = (int)blockIdx.y * R::RM;
+  const int64_t kb = (int64_t)blockIdx.z * kper;
+  const int64_t ke = (kb + kper < g.K) ? kb + kper : g.K;
+  if (kb >= ke) return;                                        // empty K slice; uniform for the CTA
+  const int jn = (g.J - j0 < R::RM) ? g.J - j0 : R::RM;
+  const int n_mma = (jn + 15) & ~15;
+  const int im = (g.I - i0 < R::RM) ? (int)(g.I - i0) : R::RM;
+  const int nkt = (int)((ke - kb + R::SK - 1) / R::SK);
+
+  const uint32_t smem0 = ptx::smem_u32(smem_raw);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NI; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&img_empty[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&img_ready[s]), kRcWorkers / 32);
+    }
+#pragma unroll
+    for (int s = 0; s < NR; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&raw_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&raw_empty[s]), kRcWorkers / 32);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 16) { ptx::tmem_alloc(ptx::smem_u32(&s_tmem), 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  if (warp == 16) {
+    // issue warp: converged, slot numbers are immediates (loop unrolled by NI)
+    const uint32_t idesc = ptx::idesc_bf16(n_mma);
+    constexpr uint64_t kHi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;                     // SBO = 128 B, descriptor version 1
+    constexpr uint32_t kLbo = ((uint32_t)(R::RM * 16) >> 4) << 16;                            // next 16-byte K chunk: 256 rows on
+    const uint32_t lo0 = (smem0 >> 4) & 0x3FFFu;
+    const bool two = im > GM;                                                                 // rows 128.. exist
+    for (int kt0 = 0; kt0 < nkt; kt0 += NI) {
+#pragma unroll
+      for (int u = 0; u < NI; ++u) {
+        const int kt = kt0 + u;
+        if (kt >= nkt) break;
+        gemm_wait(ptx::smem_u32(&img_ready[u]), (uint32_t)(kt / NI) & 1u, 4);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t img = lo0 + (uint32_t)u * (R::kImgBytes >> 4);
+          const uint64_t b_hi = kHi | (uint64_t)((img + ((2 * R::kPart) >> 4)) | kLbo);
+          const uint64_t b_lo = kHi | (uint64_t)((img + ((3 * R::kPart) >> 4)) | kLbo);
+          const uint32_t acc0 = kt > 0 ? 1u : 0u;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !two) break;
+            const uint64_t a_hi = kHi | (uint64_t)((img + h * ((GM * 16) >> 4)) | kLbo);
+            const uint64_t a_lo = kHi | (uint64_t)((img + (R::kPart >> 4) + h * ((GM * 16) >> 4)) | kLbo);
+            ptx::mma_bf16_ss(tmem + h * 256, a_lo, b_hi, idesc, acc0);
+            ptx::mma_bf16_ss(tmem + h * 256, a_hi, b_lo, idesc, 1u);
+            ptx::mma_bf16_ss(tmem + h * 256, a_hi, b_hi, idesc, 1u);
+          }
+          ptx::mma_commit(ptx::smem_u32(&img_empty[u]));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 17) {
+    if (lane == 0) {
+      ptx::prefetch_tensormap(&amap);
+      ptx::prefetch_tensormap(&bmap);
+      for (int kt = 0; kt < nkt; ++kt) {
+        const int rs = kt % NR;
+        if (kt >= NR) gemm_wait(ptx::smem_u32(&raw_empty[rs]), (uint32_t)(kt / NR - 1) & 1u, 7);
+        const uint32_t bar = ptx::smem_u32(&raw_full[rs]);
+        const uint32_t raw = smem0 + R::kRawRing + (uint32_t)rs * R::kRawBytes;
+        const int k0 = (int)(kb + (int64_t)kt * R::SK);
+        ptx::mbar_arrive_expect_tx(bar, R::kRawBytes);
+        ptx::tma_load_2d(raw, &amap, (int)i0, k0, bar);
+        ptx::tma_load_2d(raw + R::kRawOp, &bmap, j0, k0, bar);
+      }
+    }
+  } else {
+    // workers: thread = (row of A and of B, one of the step's two 8-k chunks)
+    const int row = tid & (R::RM - 1), c = tid >> 8;
+    const bool want_rowsum = g.rowsum != nullptr && blockIdx.y == 0;   // bias gradient: row sums of A (exact fp32 adds)
+    float rsum = 0.f;
+    const uint32_t rd = (uint32_t)(8 * c) * (R::RM * 4) + (uint32_t)row * 4;
+    const uint32_t wr = (uint32_t)c * (R::RM * 16) + (uint32_t)row * 16;
+    for (int kt = 0; kt < nkt; ++kt) {
+      const int rs = kt % NR, si = kt % NI;
+      const uint32_t raw = smem0 + R::kRawRing + (uint32_t)rs * R::kRawBytes + rd;
+      const uint32_t img = smem0 + (uint32_t)si * R::kImgBytes + wr;
+      gemm_wait(ptx::smem_u32(&raw_full[rs]), (uint32_t)(kt / NR) & 1u, 6);
+      float a[8], b[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        a[e] = ptx::ld_smem_f32(raw + (uint32_t)e * (R::RM * 4));
+        b[e] = ptx::ld_smem_f32(raw + R::kRawOp + (uint32_t)e * (R::RM * 4));
+      }
+      if (want_rowsum) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) rsum += a[e];
+      }
+      if (kt >= NI) gemm_wait(ptx::smem_u32(&img_empty[si]), (uint32_t)(kt / NI - 1) & 1u, 1);
+      store_chunk<8>(img, img + R::kPart, a);
+      store_chunk<8>(img + 2 * R::kPart, img + 3 * R::kPart, b);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(ptx::smem_u32(&img_ready[si]));
+        ptx::mbar_arrive(ptx::smem_u32(&raw_empty[rs]));   // behind the stores that consumed the landing slot (see the packed kernel)
+      }
+    }
+    if (want_rowsum && row < im) atomicAdd(g.rowsum + i0 + row, rsum);
+    gemm_wait(ptx::smem_u32(&img_empty[(nkt - 1) % NI]), (uint32_t)((nkt - 1) / NI) & 1u, 2);   // covers every UMMA issued before it
+    ptx::tc_fence_after();
+    const int hw = warp >> 3;                                  // warps 0-7: rows 0..127, warps 8-15: rows 128..255
+    const int im_h = im - hw * GM < GM ? im - hw * GM : GM;
+    if (im_h > 0)
+      gemm_epilogue(g, tmem + (uint32_t)hw * 256, smem0 + (uint32_t)hw * (8 * 32 * kEpiRow), warp & 7, lane, i0 + hw * GM, j0, im_h, jn,
+                    n_mma, gridDim.z > 1, blockIdx.z == 0);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 16) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 512); }
+}
+
 // ---- weights as the B operand (forward, dX): packed once per call into the stage images (hi | lo per TN-row tile and
 // K stage, zero padded) by a tiny kernel, then streamed by the TMA engine: no registers, no thread work, stages ahead.
 template <int KCH, int TN>
@@ -818,18 +979,23 @@ TensorMapEncodeFn tensor_map_encoder() {
   }();
   return fn;
 }
-bool encode_a_map(const GemmArgs& a, CUtensorMap* map) {
-  if (std::getenv("ZEST_GEMM_NO_TMA_A")) return false;           // developer A/B switch
-  if (a.sa_k != 1 || (reinterpret_cast<uintptr_t>(a.A) & 15) != 0 || (a.sa_i & 3) != 0 || a.sa_i < a.K) return false;
-  if (a.I >= (1ll << 31) || a.K >= (1ll << 31) || a.sa_i * 4 >= (1ll << 40)) return false;
+// fp32 matrix [outer, inner] with unit stride along inner and `ld` floats between outer indices -> boxes of box_inner x box_outer
+bool encode_map_2d(CUtensorMap* map, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer,
+                   CUtensorMapSwizzle swizzle) {
+  if (std::getenv("ZEST_GEMM_NO_TMA_A")) return false;           // developer A/B switch: keep the register-staged kernels
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 3) != 0 || ld < inner) return false;
+  if (inner >= (1ll << 31) || outer >= (1ll << 31) || ld * 4 >= (1ll << 40)) return false;
   const TensorMapEncodeFn enc = tensor_map_encoder();
   if (!enc) return false;
-  const cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.I};
-  const cuuint64_t strides[1] = {(cuuint64_t)a.sa_i * 4};
-  const cuuint32_t box[2] = {16, (cuuint32_t)GM};
+  const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   const cuuint32_t estr[2] = {1, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.A), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+bool encode_a_map(const GemmArgs& a, CUtensorMap* map) {   // k-contiguous A[I, K]: 16 k x 128 rows, 64-byte swizzle
+  return a.sa_k == 1 && encode_map_2d(map, a.A, a.K, a.I, a.sa_i, 16, GM, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 template <int KCH, bool AKC, bool DUAL, bool TMA_A>
@@ -875,6 +1041,44 @@ int launch_variant(const GemmArgs& a, dim3 grid, int64_t kper, cudaStream_t st) 
   ZEST_LAUNCH_CHECK();
   return ZEST_OK;
 }
+// dW-shaped GEMM (both operands row-contiguous, bf16 split): tensor-copy-fed 256 x 256 tiles, one CTA per SM.  Returns
+// ZEST_OK + launched = true, or launched = false when the operands do not qualify (the caller keeps the register kernel).
+int launch_rc_tma(const GemmArgs& a0, bool* launched, cudaStream_t st) {
+  *launched = false;
+  GemmArgs a = a0;
+  if (a.sa_i != 1 || a.sb_j != 1 || a.I <= GM || a.K >= (1ll << 31)) return ZEST_OK;
+  CUtensorMap amap, bmap;
+  if (!encode_map_2d(&amap, a.A, a.I, a.K, a.sa_k, RcRing::RM, RcRing::SK, CU_TENSOR_MAP_SWIZZLE_NONE) ||
+      !encode_map_2d(&bmap, a.B, a.J, a.K, a.sb_k, RcRing::RM, RcRing::SK, CU_TENSOR_MAP_SWIZZLE_NONE))
+    return ZEST_OK;
+  const int64_t ti = (a.I + RcRing::RM - 1) / RcRing::RM, tj = (a.J + RcRing::RM - 1) / RcRing::RM, tiles = ti * tj;
+  ZEST_CHECK_ARG(ti < (1ll << 31) && tj < 65536, "tc gemm: shape too large for one launch");
+  int64_t splits = 1;
+  if (a.splits > 1) {
+    // <= 192 chained UMMAs per accumulator (the fp32 accumulate truncates: see launch_gemm_tc) = 1024 k per CTA, and whole
+    // waves of one CTA per SM
+    const int64_t min_splits = (a.K + 1023) / 1024, sms = num_sms();
+    const int64_t waves = (min_splits * tiles + sms - 1) / sms;
+    splits = waves * sms / tiles;
+    if (splits < min_splits) splits = min_splits;
+    const int64_t max_splits = (a.K + 255) / 256;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    a.accumulate = 1;
+  }
+  int64_t kper = (a.K + splits - 1) / splits;
+  kper = (kper + 31) / 32 * 32;
+  splits = (a.K + kper - 1) / kper;
+  ZEST_CHECK_ARG(splits == 1 || (!a.Z && !a.gate && !a.relu && !a.gb_dZ), "tc gemm: split-K cannot fuse a non-linear epilogue");
+  ZEST_CHECK_ARG(splits < 65536, "tc gemm: too many K slices");
+  constexpr int kBytes = (int)(RcRing::kBytes + RcRing::kTail);
+  ZEST_CUDA(cudaFuncSetAttribute(tc_gemm_rc_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes));
+  tc_gemm_rc_tma_kernel<<<dim3((unsigned)ti, (unsigned)tj, (unsigned)splits), kRcWorkers + 64, kBytes, st>>>(a, kper, amap, bmap);
+  ZEST_LAUNCH_CHECK();
+  *launched = true;
+  return ZEST_OK;
+}
+
 template <int KCH>
 int launch_prec(const GemmArgs& a, dim3 grid, int64_t kper, cudaStream_t st) {
   const bool akc = a.sa_k == 1, bkc = a.sb_k == 1;
@@ -914,6 +1118,11 @@ int launch_gemm_tc(const GemmArgs& a0, int engine, cudaStream_t st) {
   // engine 2 keeps the long split-K reductions (dW) on the bf16 split: half the UMMAs per accumulator (less truncation
   // bias, measured) and they are leaves of the graph - nothing compounds through them
   const bool bf16 = engine == 1 || a.splits > 1;
+  if (bf16 && a.sa_i == 1 && a.sb_j == 1 && a.I > GM) {   // dW of the 256-wide layers: tensor-copy-fed kernel
+    bool launched = false;
+    const int rc = launch_rc_tma(a, &launched, st);
+    if (rc != ZEST_OK || launched) return rc;
+  }
   const int GK = bf16 ? 32 : 16;
   const int64_t ti = (a.I + GM - 1) / GM, tj = (a.J + GN - 1) / GN;
   ZEST_CHECK_ARG(ti < (1ll << 31) && tj < 65536, "tc gemm: shape too large for one launch");

@@ -262,6 +262,11 @@ __device__ __forceinline__ uint32_t mul_relu_bf16x2(uint32_t a, uint32_t b) {
   return r;
 }
 
+__device__ __forceinline__ float ld_smem_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ uint4 ld_smem_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
