@@ -29,18 +29,19 @@ static inline int64_t up4(int64_t v) { return (v + 3) & ~int64_t(3); }
 // Workspace plan: offsets in floats, every row-major [M, ld] block starts 16-byte aligned.
 struct F32Plan {
   int W, P, F, Cv, D, skip, ns;
-  int ldX5, ldVX;
-  int64_t G, X5, H[16], Z[16], VX, V128, SH, RGB;           // forward
+  int ldX5, ldVX, ldXF;
+  int64_t G, X5, XF, H[16], Z[16], VX, V128, SH, RGB;       // forward
   int64_t gHa, gHb, dZ, gG, gX5, gVX, gV128, gSH, gRGB;      // backward scratch (train only); dZ / gHb ping-pong as dZ_i
+  int64_t gWS;                                                // stacked small heads' dW [16, W] + db [16] (train only)
   int64_t PACK;                                               // weight-operand stage images of the tensor-core GEMM
   static constexpr int64_t kPackFloats = 512 * 1024;          // 2 MiB >= 2 column tiles x 22 K stages x 32 KiB
   int64_t total;
   F32Plan(const zest_net* n, int64_t M, bool train) {
     W = n->width; P = n->in_pts; F = n->in_feat; Cv = n->in_views; D = n->depth; skip = n->skip; ns = n->n_small;
-    ldX5 = (int)up4(P + W); ldVX = (int)up4(W + Cv);
+    ldX5 = (int)up4(P + W); ldVX = (int)up4(W + Cv); ldXF = (int)up4(F);
     int64_t o = 0;
     auto take = [&](int64_t per_row) { int64_t r = o; o += up4(M * per_row); return r; };
-    G = take(W); X5 = take(ldX5);
+    G = take(W); X5 = take(ldX5); XF = take(ldXF);
     if (train) {
       for (int i = 0; i < D; ++i) { H[i] = (i == skip) ? -1 : take(W); Z[i] = take(W); }
     } else {
@@ -51,6 +52,7 @@ struct F32Plan {
     if (train) {
       gHa = take(W); gHb = take(W); dZ = take(W); gG = take(W); gX5 = take(ldX5); gVX = take(ldVX);
       gV128 = take(W / 2); gSH = take(16); gRGB = take(4);
+      gWS = o; o += up4(16 * (int64_t)W + 16);
     }
     PACK = o; o += kPackFloats;
     total = o;
@@ -63,6 +65,14 @@ struct PackScope {
   PackScope(float* ws, const F32Plan& p) { t_pack = ws + p.PACK; }
   ~PackScope() { t_pack = nullptr; }
 };
+
+// rows [r0, r0 + n) of the stacked heads' dW / db -> += into one head's gradient tensors (zero-initialised by the caller)
+__global__ void heads_scatter_kernel(const float* __restrict__ gws, int W, int r0, int n, float* __restrict__ gW,
+                                     float* __restrict__ gb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gW && i < n * W) gW[i] += gws[r0 * W + i];
+  if (gb && i < n) gb[i] += gws[16 * W + r0 + i];
+}
 
 __global__ void finalize_fwd_kernel(const float* __restrict__ rgb, const float* __restrict__ sh, int kind,
                                     int64_t M, float* __restrict__ raw, int out_ch) {
@@ -245,9 +255,14 @@ extern "C" int zest_mlp_fwd_f32(const zest_net* net, const float* x, int ldx, in
   const int W = p.W, P = p.P;
   float* G = ws + p.G;
   float* X5 = ws + p.X5;
-  { GemmArgs a = linear(x + P, ldx, w + net->w_gate, W, p.F, w + net->b_gate, G, W, M); ZEST_TRY(launch_gemm(a, st)); }
+  float* XF = ws + p.XF;
+  // The caller's rows are [pe | feat | views] back to back (110 floats: neither the feat block nor the rows are 16-byte
+  // aligned), which keeps the tensor-core GEMMs off their tensor-copy operand path.  pe is copied into the skip buffer
+  // anyway; feat gets an aligned copy of its own (M x 20 floats), and layer 0 / the gate read those.
   ZEST_TRY(copy2d(X5, p.ldX5, x, ldx, P, M, st));
-  const float* in = x; int64_t ld_in = ldx;
+  ZEST_TRY(copy2d(XF, p.ldXF, x + P, ldx, p.F, M, st));
+  { GemmArgs a = linear(XF, p.ldXF, w + net->w_gate, W, p.F, w + net->b_gate, G, W, M); ZEST_TRY(launch_gemm(a, st)); }
+  const float* in = X5; int64_t ld_in = p.ldX5;
   for (int i = 0; i < p.D; ++i) {
     float* out = (i == p.skip) ? X5 + P : ws + p.H[i];
     const int64_t ld_out = (i == p.skip) ? p.ldX5 : W;
@@ -304,12 +319,20 @@ extern "C" int zest_mlp_bwd_f32(const zest_net* net, const float* x, int ldx, in
   // feature_linear and the stacked small heads feed gH of the last layer
   if (gp(I_FEAT)) ZEST_TRY(launch_gemm(linear_bwd_w(gVX, p.ldVX, W, Hl, ldHl, W, gp(I_FEAT), M, gp(I_FEAT + 1)), st));
   ZEST_TRY(launch_gemm(linear_bwd_x(gVX, p.ldVX, w + net->w_feat, W, W, gHa, W, M, 0), st));
-  if (gp(I_ALPHA)) ZEST_TRY(launch_gemm(linear_bwd_w(gSH, 16, 1, Hl, ldHl, W, gp(I_ALPHA), M, gp(I_ALPHA + 1)), st));
-  if (net->kind == 1 && gp(I_EXTRA)) {
-    ZEST_TRY(launch_gemm(linear_bwd_w(gSH + 1, 16, 1, Hl, ldHl, W, gp(I_EXTRA), M, gp(I_EXTRA + 1)), st));
-  } else if (net->kind == 2 && gp(I_EXTRA)) {
-    ZEST_TRY(launch_gemm(linear_bwd_w(gSH + 1, 16, 6, Hl, ldHl, W, gp(I_EXTRA), M, gp(I_EXTRA + 1)), st));
-    ZEST_TRY(launch_gemm(linear_bwd_w(gSH + 7, 16, 2, Hl, ldHl, W, gp(I_EXTRA + 2), M, gp(I_EXTRA + 3)), st));
+  // The small heads (alpha; + blending; + scene flow, disocclusion) are one stacked [ns, W] weight in the forward and one
+  // dW GEMM here (each used to stream the last hidden activation on its own): [ns, W] + [ns] into scratch, then scattered.
+  if (gp(I_ALPHA) || gp(I_EXTRA) || (net->kind == 2 && gp(I_EXTRA + 2))) {
+    float* gWS = ws + p.gWS;
+    ZEST_CUDA(cudaMemsetAsync(gWS, 0, (size_t)(16 * W + 16) * sizeof(float), st));
+    ZEST_TRY(launch_gemm(linear_bwd_w(gSH, 16, p.ns, Hl, ldHl, W, gWS, M, gWS + 16 * W), st));
+    auto scatter = [&](int r0, int n, int idx) {
+      if (!gp(idx) && !gp(idx + 1)) return;
+      heads_scatter_kernel<<<(unsigned)((n * W + 255) / 256), 256, 0, st>>>(gWS, W, r0, n, gp(idx), gp(idx + 1));
+    };
+    scatter(0, 1, I_ALPHA);
+    if (net->kind == 1) scatter(1, 1, I_EXTRA);
+    if (net->kind == 2) { scatter(1, 6, I_EXTRA); scatter(7, 2, I_EXTRA + 2); }
+    ZEST_LAUNCH_CHECK();
   }
   // Every GEMM that produces the gradient wrt a hidden activation h_i = relu(z_i * g) applies that layer's gate backward in
   // its epilogue (GemmArgs::gb_*): it writes dZ_i = gH_i 1[z_i g > 0] g and accumulates gG += gH_i 1[..] z_i; gH_i itself
@@ -328,7 +351,7 @@ extern "C" int zest_mlp_bwd_f32(const zest_net* net, const float* x, int ldx, in
   for (int i = D - 1; i >= 0; --i) {
     // layer input
     const float* in; int64_t ld_in; const int K = in_layer(net, i);
-    if (i == 0) { in = x; ld_in = ldx; }
+    if (i == 0) { in = X5; ld_in = p.ldX5; }          // the aligned copy of pe (forward)
     else if (i == p.skip + 1) { in = X5; ld_in = p.ldX5; }
     else { in = (i - 1 == p.skip) ? X5 + P : ws + p.H[i - 1]; ld_in = (i - 1 == p.skip) ? p.ldX5 : W; }
     if (gp(2 * i)) ZEST_TRY(launch_gemm(linear_bwd_w(dZ_cur, W, W, in, ld_in, K, gp(2 * i), M, gp(2 * i + 1)), st));
@@ -349,7 +372,7 @@ extern "C" int zest_mlp_bwd_f32(const zest_net* net, const float* x, int ldx, in
     }
   }
   // gate (pts_bias)
-  if (gp(I_GATE)) ZEST_TRY(launch_gemm(linear_bwd_w(gG, W, W, x + P, ldx, p.F, gp(I_GATE), M, gp(I_GATE + 1)), st));
+  if (gp(I_GATE)) ZEST_TRY(launch_gemm(linear_bwd_w(gG, W, W, ws + p.XF, p.ldXF, p.F, gp(I_GATE), M, gp(I_GATE + 1)), st));
   if (gx) {
     ZEST_TRY(launch_gemm(linear_bwd_x(gG, W, w + net->w_gate, W, p.F, gx + P, ldx, M, 0), st));
     ZEST_TRY(copy2d(gx + P + p.F, ldx, gVX + W, p.ldVX, p.Cv, M, st));
