@@ -17,17 +17,22 @@
 // taking the same GemmArgs / fused epilogue (bias, pre-gate copy, gate, ReLU, accumulate, split-K atomics) as the
 // CUDA-core sgemm_kernel it replaces; the exact-fp32 SIMT kernel stays selectable (zest_set_gemm_engine).
 //
-// Two kernels, both with two CTAs per SM (96 KB smem, 256 TMEM columns each: one CTA's epilogue runs under the other's
-// main loop) and K stages of four 16-byte chunks per row and part (32 k as bf16, 16 k as tf32):
+// Three kernels; K stages of 16-byte chunks per row and part (32 k as bf16, 16 k as tf32):
 //   tc_gemm_packed_kernel  B is a weight matrix every row tile re-reads (forward, dX): packed once per call into the UMMA
-//                          stage images and streamed by TMA; eight worker warps stage A through registers (static register
-//                          sets, up to 6 stages ahead) and run the epilogue, a ninth warp drives the TMA and issues the
-//                          UMMAs (converged warp, warp-uniform descriptors); mbarriers only in the main loop.
+//                          stage images and streamed by bulk copies.  Two CTAs per SM (<= 112.25 KB smem, 256 TMEM columns
+//                          each: one CTA's epilogue runs under the other's main loop).  A arrives by 2-D tensor copies into
+//                          a landing ring (a tenth warp), eight worker warps split it into the hi / lo images and run the
+//                          epilogue, a ninth warp drives the weight copies and issues the UMMAs (converged warp, warp-
+//                          uniform descriptors); mbarriers only in the main loop.  Operands that do not qualify for a
+//                          tensor map are staged through registers (static register sets, up to 6 stages ahead).
 //                          128 x 256 tiles, or 128 x 128 with separate head / cross accumulators (engine 2).
-//   tc_gemm_kernel         both operands are activations (dW, split-K): all 256 threads stage A and B through registers into
-//                          the K-major no-swizzle images (core matrix = 8 rows x 16 B, the MLP kernel's layout), thread 0
-//                          issues 6 UMMAs per stage (2 K steps x 3 products) and commits to the stage's "empty" mbarrier;
-//                          the bias gradient (row sums of A) rides along in the staging threads.
+//   tc_gemm_rc_tma_kernel  both operands are [samples, features] activations and the reduction is long (dW): one CTA per SM
+//                          owns a 256 x 256 tile (512 TMEM columns) and a K slice; both operands land by tensor copies, 16
+//                          worker warps transpose + split them out of shared memory, split-K joined by vector atomics.
+//   tc_gemm_kernel         everything else (dW of the narrow heads, unaligned operands): all 256 threads stage A and B
+//                          through registers into the K-major no-swizzle images (core matrix = 8 rows x 16 B, the MLP
+//                          kernel's layout), thread 0 issues 6 UMMAs per stage (2 K steps x 3 products) and commits to the
+//                          stage's "empty" mbarrier; the bias gradient (row sums of A) rides along in the staging threads.
 // Epilogue (shared): tcgen05.ld 32 columns per warp pass (lane = row), per-warp shared-memory transpose, fused ops (bias,
 // Z copy, gate, ReLU, accumulate, the gate backward of the layer below, vector atomics for split-K), global accesses in
 // which a warp covers 4 rows x 128 contiguous bytes, every load of a row batch issued before its first use.
