@@ -125,7 +125,8 @@ def test_tc_gemm_matches_fp32(zops, lib, I, J, K, a_kc, b_kc):
     assert e_bf16 <= 3e-5, f"3 x bf16 GEMM error {e_bf16:.2e} (SIMT fp32: {e_simt:.2e})"
 
 
-@pytest.mark.parametrize("I,K,lda", [(2048, 256, 256), (2085, 256, 256), (1536, 320, 320), (1100, 319, 320)])
+@pytest.mark.parametrize("I,K,lda", [(2048, 256, 256), (2085, 256, 256), (1536, 320, 320), (1100, 319, 320),
+                                     (4096 * 128, 256, 256)])     # the training shape: 8192 CTAs, two per SM
 def test_tc_gemm_identity_exact(zops, lib, I, K, lda):
     """C = A x Identity^T on the default engine must return A bit for bit (integers are exact in hi + lo): every element is its
     own witness of which (row, k) of A the kernel staged.  Regression test of the tensor-copy-fed A path (tc_gemm.cu): a landing
@@ -141,8 +142,27 @@ def test_tc_gemm_identity_exact(zops, lib, I, K, lda):
     for rep in range(3):                  # the bug was a race: a few launches
         Cm = torch.full((I, K), -1.0, device=DEV)
         _gemm(lib, Ad, (lda, 1), Bd, (K, 1), Cm, I, K, K, engine=2, scratch=scratch)
-        bad = int((Cm.cpu() != A[:, :K]).sum())
+        bad = int((Cm != Ad[:, :K]).sum())
         assert bad == 0, f"{bad} elements of A staged wrong (rep {rep})"
+
+
+@pytest.mark.parametrize("I,J", [(256, 256), (256, 319), (200, 63)])
+def test_tc_gemm_dw_full_size_exact(zops, lib, I, J):
+    """The weight-gradient GEMM at the training size (K = 4096 rays x 128 samples, split-K, tensor-copy-fed 256-row tiles):
+    dZ = one-hot rows, H = small integers, so every product, every TMEM accumulation and every cross-CTA atomic is exact in fp32
+    and the result must equal the integer reference bit for bit (tc_gemm.cu: tc_gemm_rc_tma_kernel)."""
+    K = 4096 * 128
+    k = torch.arange(K, device=DEV)
+    A = torch.zeros((K, I), device=DEV)
+    A[k, k % I] = 1.0
+    ldb = (J + 3) // 4 * 4
+    Bm = torch.full((K, ldb), float("nan"), device=DEV)
+    Bm[:, :J] = ((k[:, None] + torch.arange(J, device=DEV)[None, :]) % 7).float()
+    want = torch.zeros((I, J), dtype=torch.float64, device=DEV).index_add_(0, k % I, Bm[:, :J].double())
+    for rep in range(2):
+        Cm = torch.zeros((I, J), device=DEV)
+        _gemm(lib, A, (1, I), Bm, (1, ldb), Cm, I, J, K, accumulate=1, splits=256, engine=2)
+        assert torch.equal(Cm.double(), want), f"dW differs: max |diff| {float((Cm.double() - want).abs().max())} (rep {rep})"
 
 
 @pytest.mark.parametrize("engine", [1, 2])
