@@ -23,12 +23,15 @@ def timeline(label, sb, engine):
         rc = lib.zest_gemm_f32(C.c_void_p(X.data_ptr()), 256, 1, C.c_void_p(W.data_ptr()), sb[0], sb[1], C.c_void_p(Y.data_ptr()), 256,
                                M, 256, 256, None, 0, 1, engine, C.c_void_p(SCRATCH.data_ptr()), SCRATCH.numel(), st())
         assert rc == 0, lib.zest_last_error()
-    buf = (C.c_ulonglong * 1024)()
-    lib.zest_gemm_read_timeline.argtypes = [C.c_void_p]
-    assert lib.zest_gemm_read_timeline(buf) == 0
+    buf = (C.c_ulonglong * (512 * 1024))()
+    meta = (C.c_int * (512 * 8))()
+    lib.zest_gemm_read_timeline.argtypes = [C.c_void_p, C.c_void_p]
+    n = lib.zest_gemm_read_timeline(buf, meta)
+    assert n > 0
+    base = ((n - 1) % 512) * 1024          # the last launch
     print(f"== {label} engine={engine}")
     for b in range(8):
-        t = [buf[b * 128 + i] for i in range(128)]
+        t = [buf[base + b * 128 + i] for i in range(128)]
         print("  cta", 1000 + b, " ".join(f"{NAMES[i]}={t[i] - t[0]}" for i in (1, 2, 6, 3, 7, 4, 5, 8)))
         if b < 2:      # per stage: slot free seen by warp 0 / its stores issued / its arrive done / issuer saw the stage ready
             for kt in range(24):

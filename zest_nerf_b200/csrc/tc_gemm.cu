@@ -231,6 +231,14 @@ struct StageRC {
   }
 };
 
+// Global accesses of the fused gate backward: L2-only loads / stores (nothing here is re-read through L1) and the gate
+// gradient accumulated by a vector reduction (red.global.add.v4.f32: one round-to-nearest add per element per kernel, the same
+// bits as load + add + store except that the reduction flushes denormals, one stream less in flight).  Measured inside a fine-tune step (tools/gemm_timeline_step.py): the
+// dX kernels' CTA lifetime 56.0 k -> 50.3 k cycles; the hints alone 3 %, larger load batches nothing - the epilogue is bound
+// by the memory system's throughput on this 3-read / 2-write mix (~4.5 TB/s), not by latency.
+__device__ __forceinline__ float4 epi_ld(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void epi_st(float* p, float4 v) { __stcg(reinterpret_cast<float4*>(p), v); }
+
 // ---- epilogue (8 warps).  Warp w owns TMEM lanes 32 (w % 4) .. +31 (rows) and the 32-column passes w / 4, w / 4 + 2, ...
 // tcgen05.ld gives lane = row; a per-warp shared-memory transpose (the stage buffers are free by now) turns that into
 // lane = (row % 4, 4 consecutive columns) so that every global access of a warp covers 4 rows x 128 contiguous bytes.
@@ -304,23 +312,23 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs& g, uint32_t tmem, 
       continue;
     }
     if (fast) {                    // fused gate backward (see GemmArgs): v [+ C] -> dZ, gG
+      constexpr int RG = 4;                   // row groups (of 4 rows) whose loads are in flight together (8: no faster)
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float4 zz[4], gg[4], acc[4];
+      for (int h = 0; h < 8 / RG; ++h) {
+        float4 zz[RG], gg[RG];
 #pragma unroll
-        for (int r2 = 0; r2 < 4; ++r2) {
-          const int row = q * 32 + (h * 4 + r2) * 4 + rsub;
+        for (int r2 = 0; r2 < RG; ++r2) {
+          const int row = q * 32 + (h * RG + r2) * 4 + rsub;
           const int64_t i = i0 + row, o = i * g.gb_ld + jj;
-          zz[r2] = gg[r2] = acc[r2] = make_float4(0.f, 0.f, 0.f, 0.f);
+          zz[r2] = gg[r2] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (row < im) {
-            zz[r2] = __ldg(reinterpret_cast<const float4*>(g.gb_Z + o));
-            gg[r2] = __ldg(reinterpret_cast<const float4*>(g.gb_G + o));
-            acc[r2] = *reinterpret_cast<const float4*>(g.gb_gG + o);
+            zz[r2] = epi_ld(g.gb_Z + o);
+            gg[r2] = epi_ld(g.gb_G + o);
           }
         }
 #pragma unroll
-        for (int r2 = 0; r2 < 4; ++r2) {
-          const int lr = (h * 4 + r2) * 4 + rsub, row = q * 32 + lr;
+        for (int r2 = 0; r2 < RG; ++r2) {
+          const int lr = (h * RG + r2) * 4 + rsub, row = q * 32 + lr;
           const uint4 w = ptx::ld_smem_v4(stg + (uint32_t)lr * kEpiRow + cq * 4);
           if (row >= im) continue;
           const int64_t o = (i0 + row) * g.gb_ld + jj;
@@ -330,9 +338,8 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs& g, uint32_t tmem, 
           const float v2 = __uint_as_float(w.z) + b4[2] + o4.z, v3 = __uint_as_float(w.w) + b4[3] + o4.w;
           const float m0 = (zz[r2].x * gg[r2].x > 0.f) ? v0 : 0.f, m1 = (zz[r2].y * gg[r2].y > 0.f) ? v1 : 0.f;
           const float m2 = (zz[r2].z * gg[r2].z > 0.f) ? v2 : 0.f, m3 = (zz[r2].w * gg[r2].w > 0.f) ? v3 : 0.f;
-          *reinterpret_cast<float4*>(g.gb_dZ + o) = make_float4(m0 * gg[r2].x, m1 * gg[r2].y, m2 * gg[r2].z, m3 * gg[r2].w);
-          *reinterpret_cast<float4*>(g.gb_gG + o) = make_float4(acc[r2].x + m0 * zz[r2].x, acc[r2].y + m1 * zz[r2].y,
-                                                                acc[r2].z + m2 * zz[r2].z, acc[r2].w + m3 * zz[r2].w);
+          epi_st(g.gb_dZ + o, make_float4(m0 * gg[r2].x, m1 * gg[r2].y, m2 * gg[r2].z, m3 * gg[r2].w));
+          atomicAdd(reinterpret_cast<float4*>(g.gb_gG + o), make_float4(m0 * zz[r2].x, m1 * zz[r2].y, m2 * zz[r2].z, m3 * zz[r2].w));
         }
       }
       __syncwarp();
@@ -703,8 +710,12 @@ __global__ void gemm_pack_b_kernel(const float* __restrict__ B, int64_t sb_j, in
 constexpr int kWorkers = 256;              // warps 0..7 stage A and run the epilogue; warp 8 drives the TMA and the UMMAs
 
 #ifdef ZEST_GEMM_TIMELINE     // developer build: clock64 stamps of CTAs 1000..1007 of the packed kernel (tools/gemm_timeline.py)
-__device__ unsigned long long g_gemm_tl[8 * 128];
-#define GTL(slot, cond) do { if (blockIdx.x >= 1000 && blockIdx.x < 1008 && (cond)) g_gemm_tl[(blockIdx.x - 1000) * 128 + (slot)] = clock64(); } while (0)
+constexpr int kTlLaunches = 512;
+__device__ unsigned long long g_gemm_tl[kTlLaunches * 8 * 128];
+__device__ int g_gemm_tl_launch;      // which launch of the packed kernel is running (set stream-ordered by the host)
+#define GTL(slot, cond) do { if (blockIdx.x >= 1000 && blockIdx.x < 1008 && (cond)) g_gemm_tl[((size_t)g_gemm_tl_launch * 8 + (blockIdx.x - 1000)) * 128 + (slot)] = clock64(); } while (0)
+int g_tl_count = 0;
+int g_tl_meta[kTlLaunches][8];
 #else
 #define GTL(slot, cond) do { } while (0)
 #endif
@@ -1007,6 +1018,15 @@ template <int KCH, bool AKC, bool DUAL, bool TMA_A>
 int launch_packed_variant(const GemmArgs& a, dim3 grid, const CUtensorMap& amap, cudaStream_t st) {
   // the attribute is per device: set it on every launch (a few hundred ns) rather than once per process
   constexpr int kBytes = (int)(PackedRing<DUAL, TMA_A>::kBytes + PackedRing<DUAL, TMA_A>::kTail);
+#ifdef ZEST_GEMM_TIMELINE
+  {
+    const int slot = g_tl_count % kTlLaunches;
+    const int meta[8] = {(int)grid.x, a.Z != nullptr, a.gate != nullptr, a.gb_dZ != nullptr, a.accumulate, a.J, (int)a.K, TMA_A ? 1 : 0};
+    std::memcpy(g_tl_meta[slot], meta, sizeof(meta));
+    ZEST_CUDA(cudaMemcpyToSymbolAsync(g_gemm_tl_launch, &slot, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+    ++g_tl_count;
+  }
+#endif
   ZEST_CUDA(cudaFuncSetAttribute(tc_gemm_packed_kernel<KCH, AKC, DUAL, TMA_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes));
   tc_gemm_packed_kernel<KCH, AKC, DUAL, TMA_A><<<grid, kWorkers + (TMA_A ? 64 : 32), kBytes, st>>>(a, (const uint8_t*)a.b_scratch, amap);
   ZEST_LAUNCH_CHECK();
@@ -1160,10 +1180,13 @@ int launch_gemm_tc(const GemmArgs& a0, int engine, cudaStream_t st) {
 using namespace zest;
 
 #ifdef ZEST_GEMM_TIMELINE
-extern "C" int zest_gemm_read_timeline(unsigned long long* host_out) {
+// stamps of the last min(count, 512) launches of the packed kernel: out[launch % 512][cta 0..7][128], meta[launch % 512][8] =
+// {grid, has Z, has gate, has fused gate backward, accumulate, J, K, tensor-copy-fed}; returns the launch count
+extern "C" int zest_gemm_read_timeline(unsigned long long* host_out, int* meta_out) {
   ZEST_CUDA(cudaDeviceSynchronize());
-  ZEST_CUDA(cudaMemcpyFromSymbol(host_out, g_gemm_tl, sizeof(unsigned long long) * 8 * 128));
-  return ZEST_OK;
+  ZEST_CUDA(cudaMemcpyFromSymbol(host_out, g_gemm_tl, sizeof(unsigned long long) * kTlLaunches * 8 * 128));
+  std::memcpy(meta_out, g_tl_meta, sizeof(g_tl_meta));
+  return g_tl_count;
 }
 #endif
 
