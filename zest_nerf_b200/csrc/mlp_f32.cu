@@ -43,7 +43,9 @@ struct F32Plan {
     auto take = [&](int64_t per_row) { int64_t r = o; o += up4(M * per_row); return r; };
     G = take(W); X5 = take(ldX5); XF = take(ldXF);
     if (train) {
-      for (int i = 0; i < D; ++i) { H[i] = (i == skip) ? -1 : take(W); Z[i] = take(W); }
+      // the backward needs z only where the layer's output is not a 16-byte-aligned [M, W] block of its own: the skip layer
+      // (its h lives behind pe in X5); everywhere else z is recovered from h (GemmArgs::gb_from_h) and never stored
+      for (int i = 0; i < D; ++i) { H[i] = (i == skip) ? -1 : take(W); Z[i] = (i == skip) ? take(W) : -1; }
     } else {
       const int64_t a = take(W), b = take(W);
       for (int i = 0; i < D; ++i) { H[i] = (i == skip) ? -1 : ((i & 1) ? b : a); Z[i] = -1; }
@@ -268,7 +270,7 @@ extern "C" int zest_mlp_fwd_f32(const zest_net* net, const float* x, int ldx, in
     const int64_t ld_out = (i == p.skip) ? p.ldX5 : W;
     GemmArgs a = linear(in, ld_in, w + net->w_pts[i], W, in_layer(net, i), w + net->b_pts[i], out, ld_out, M);
     a.gate = G; a.ldg = W; a.relu = 1;
-    if (train) { a.Z = ws + p.Z[i]; a.ldz = W; }
+    if (train && p.Z[i] >= 0) { a.Z = ws + p.Z[i]; a.ldz = W; }
     ZEST_TRY(launch_gemm(a, st));
     if (i == p.skip) { in = X5; ld_in = p.ldX5; } else { in = out; ld_in = ld_out; }
   }
@@ -341,7 +343,8 @@ extern "C" int zest_mlp_bwd_f32(const zest_net* net, const float* x, int ldx, in
   float* dZ_cur = dZ;
   float* dZ_next = gHb;
   auto fuse_gate = [&](GemmArgs& a, int layer, int col0, float* out) {
-    a.gb_Z = ws + p.Z[layer]; a.gb_G = G; a.gb_gG = gG; a.gb_dZ = out; a.gb_ld = W; a.gb_col0 = col0;
+    a.gb_from_h = p.Z[layer] < 0;
+    a.gb_Z = ws + (a.gb_from_h ? p.H[layer] : p.Z[layer]); a.gb_G = G; a.gb_gG = gG; a.gb_dZ = out; a.gb_ld = W; a.gb_col0 = col0;
   };
   {
     GemmArgs a = linear_bwd_x(gSH, 16, w + net->w_small, p.ns, W, gHa, W, M, 1);   // + feature_linear's part already in gHa

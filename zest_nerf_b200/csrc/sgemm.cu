@@ -122,9 +122,10 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
         if (g.accumulate) v += *c;
         const int64_t o = i * g.gb_ld + (j - g.gb_col0);
         const float zz = __ldg(g.gb_Z + o), gg = __ldg(g.gb_G + o);
-        const float m = (zz * gg > 0.f) ? v : 0.f;
+        const bool on = g.gb_from_h ? (zz > 0.f) : (zz * gg > 0.f);
+        const float m = on ? v : 0.f;
         g.gb_dZ[o] = m * gg;
-        g.gb_gG[o] += m * zz;
+        g.gb_gG[o] += m * gate_bwd_z(zz, gg, on, g.gb_from_h);
         continue;
       }
       if (atomic) atomicAdd(c, v);

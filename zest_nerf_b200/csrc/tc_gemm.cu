@@ -336,10 +336,14 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs& g, uint32_t tmem, 
           if (g.accumulate) o4 = *reinterpret_cast<const float4*>(g.C + (i0 + row) * g.ldc + j);   // last layer only: read at use
           const float v0 = __uint_as_float(w.x) + b4[0] + o4.x, v1 = __uint_as_float(w.y) + b4[1] + o4.y;
           const float v2 = __uint_as_float(w.z) + b4[2] + o4.z, v3 = __uint_as_float(w.w) + b4[3] + o4.w;
-          const float m0 = (zz[r2].x * gg[r2].x > 0.f) ? v0 : 0.f, m1 = (zz[r2].y * gg[r2].y > 0.f) ? v1 : 0.f;
-          const float m2 = (zz[r2].z * gg[r2].z > 0.f) ? v2 : 0.f, m3 = (zz[r2].w * gg[r2].w > 0.f) ? v3 : 0.f;
+          const int fh = g.gb_from_h;
+          const bool on0 = fh ? zz[r2].x > 0.f : zz[r2].x * gg[r2].x > 0.f, on1 = fh ? zz[r2].y > 0.f : zz[r2].y * gg[r2].y > 0.f;
+          const bool on2 = fh ? zz[r2].z > 0.f : zz[r2].z * gg[r2].z > 0.f, on3 = fh ? zz[r2].w > 0.f : zz[r2].w * gg[r2].w > 0.f;
+          const float m0 = on0 ? v0 : 0.f, m1 = on1 ? v1 : 0.f, m2 = on2 ? v2 : 0.f, m3 = on3 ? v3 : 0.f;
           epi_st(g.gb_dZ + o, make_float4(m0 * gg[r2].x, m1 * gg[r2].y, m2 * gg[r2].z, m3 * gg[r2].w));
-          atomicAdd(reinterpret_cast<float4*>(g.gb_gG + o), make_float4(m0 * zz[r2].x, m1 * zz[r2].y, m2 * zz[r2].z, m3 * zz[r2].w));
+          atomicAdd(reinterpret_cast<float4*>(g.gb_gG + o),
+                    make_float4(m0 * gate_bwd_z(zz[r2].x, gg[r2].x, on0, fh), m1 * gate_bwd_z(zz[r2].y, gg[r2].y, on1, fh),
+                                m2 * gate_bwd_z(zz[r2].z, gg[r2].z, on2, fh), m3 * gate_bwd_z(zz[r2].w, gg[r2].w, on3, fh)));
         }
       }
       __syncwarp();
@@ -369,10 +373,13 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs& g, uint32_t tmem, 
           const float4 zz = __ldg(reinterpret_cast<const float4*>(g.gb_Z + o));
           const float4 gg = __ldg(reinterpret_cast<const float4*>(g.gb_G + o));
           float4 acc = *reinterpret_cast<const float4*>(g.gb_gG + o);
-          const float m0 = (zz.x * gg.x > 0.f) ? v[0] : 0.f, m1 = (zz.y * gg.y > 0.f) ? v[1] : 0.f;
-          const float m2 = (zz.z * gg.z > 0.f) ? v[2] : 0.f, m3 = (zz.w * gg.w > 0.f) ? v[3] : 0.f;
+          const int fh = g.gb_from_h;
+          const bool on0 = fh ? zz.x > 0.f : zz.x * gg.x > 0.f, on1 = fh ? zz.y > 0.f : zz.y * gg.y > 0.f;
+          const bool on2 = fh ? zz.z > 0.f : zz.z * gg.z > 0.f, on3 = fh ? zz.w > 0.f : zz.w * gg.w > 0.f;
+          const float m0 = on0 ? v[0] : 0.f, m1 = on1 ? v[1] : 0.f, m2 = on2 ? v[2] : 0.f, m3 = on3 ? v[3] : 0.f;
           *reinterpret_cast<float4*>(g.gb_dZ + o) = make_float4(m0 * gg.x, m1 * gg.y, m2 * gg.z, m3 * gg.w);
-          acc.x += m0 * zz.x; acc.y += m1 * zz.y; acc.z += m2 * zz.z; acc.w += m3 * zz.w;
+          acc.x += m0 * gate_bwd_z(zz.x, gg.x, on0, fh); acc.y += m1 * gate_bwd_z(zz.y, gg.y, on1, fh);
+          acc.z += m2 * gate_bwd_z(zz.z, gg.z, on2, fh); acc.w += m3 * gate_bwd_z(zz.w, gg.w, on3, fh);
           *reinterpret_cast<float4*>(g.gb_gG + o) = acc;
         } else {
 #pragma unroll
@@ -380,9 +387,10 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs& g, uint32_t tmem, 
             if (t >= nv) continue;
             if (j + t < g.gb_col0) { c[t] = v[t]; continue; }     // (v already holds C + acc when accumulating)
             const float zz = __ldg(g.gb_Z + o + t), gg = __ldg(g.gb_G + o + t);
-            const float m = (zz * gg > 0.f) ? v[t] : 0.f;
+            const bool on = g.gb_from_h ? (zz > 0.f) : (zz * gg > 0.f);
+            const float m = on ? v[t] : 0.f;
             g.gb_dZ[o + t] = m * gg;
-            g.gb_gG[o + t] += m * zz;
+            g.gb_gG[o + t] += m * gate_bwd_z(zz, gg, on, g.gb_from_h);
           }
         }
         continue;
