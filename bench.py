@@ -562,10 +562,22 @@ def fine_tune_report(res, V, pk, rays=4096):
     flop_per_ray = 3 * 2.0 * (ms_s + 3 * ms_d) * S
     peak = pk["bf16_tflops_sustained"]
     rep = {"rays_per_step": rays, "flop_per_ray": flop_per_ray, "roofline_rays_per_s": peak * 1e12 / flop_per_ray, "engines": {}}
+    # The second bound, and the one the layer-by-layer fp32 structure actually runs against: every layer
+    # GEMM streams [samples, 256] fp32 activations through HBM.  Streams of samples x 256 x 4 B per 256-wide layer and pass:
+    # forward 3 (input, gate, output), dX 6 (dZ in, h, gate, gate-gradient read + write, dZ out), dW 2 (dZ, input) = 11; 8 layers
+    # + ~10 for the gate, feature, views and head layers = 98 per pass; 1 static + 3 dynamic passes.
+    streams, passes = 98, 4
+    gb = streams * passes * rays * S * 256 * 4 / 1e9
+    floor_ms = gb / pk["hbm_gbs"] * 1e3
+    rep["layerwise_hbm_floor"] = {"gb_per_step": round(gb, 1), "streams_per_pass": streams, "peak_gbs": pk["hbm_gbs"], "ms_per_step": round(floor_ms, 2),
+                                  "per_kernel": "ncu inside a step (profiles/r02_ncu_tc_gemm_train_summary.txt): dX GEMM + fused gate backward 3.18 GB in "
+                                                "0.656 ms = 4.85 TB/s (0.74 of the copy bandwidth), dW GEMM 1.08 GB in 0.210 ms = 5.1 TB/s (0.79); DRAM "
+                                                "traffic = the algorithmic bytes in both"}
     for e, r in res.items():
         rep["engines"][FT_ENGINE_NAMES[e]] = {"ms_per_step": round(r["ms_per_step"], 2), "rays_per_s": round(r["rays_per_s"], 1),
                                               "algorithmic_tflops": round(r["rays_per_s"] * flop_per_ray / 1e12, 1),
                                               "frac_of_bf16_tensor_roofline": round(r["rays_per_s"] * flop_per_ray / 1e12 / peak, 4),
+                                              "frac_of_layerwise_hbm_floor": round(floor_ms / r["ms_per_step"], 3),
                                               "gpu_launches_per_step": int(r["gpu_launches_per_step"])}
     return rep
 
