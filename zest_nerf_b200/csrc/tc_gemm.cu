@@ -5,7 +5,7 @@
 //     A*B ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi
 //
 //   engine 1: bf16 head + bf16 residual (16 mantissa bits), one accumulator
-//   engine 2: tf32 head + tf32 residual, both round-to-nearest (22 mantissa bits, twice the tensor-pipe time); the
+//   engine 2: tf32 head (round to nearest) + fp32 residual read as tf32 (21-22 mantissa bits, twice the tensor-pipe time); the
 //             weight-operand GEMMs (forward, dX) keep the head product and the cross products in two accumulators
 // Measured against fp64 (tests/test_gpu_parity.py), K = 256..347, one accumulator: fp32 SIMT 6e-7, 3 x tf32 2-3.5e-6,
 // 3 x bf16 4-6e-6 of max|C|; unsplit K = 5000: 3.2e-6 / 3.7e-5 / 1.8e-5.  The tensor core's fp32 accumulate TRUNCATES:
@@ -73,7 +73,9 @@ __device__ __forceinline__ void gemm_wait(uint32_t bar, uint32_t parity, int tag
 }
 
 #ifndef ZEST_TF32_SPLIT
-#define ZEST_TF32_SPLIT 0   // 0: cvt.rna head and residual; 1 / 2: integer-rounded head, masked / raw residual (same measured error and time)
+#define ZEST_TF32_SPLIT 2   // 2: head = (bits + 0x1000) & ~0x1fff (round to nearest, ties away = cvt.rna on finite values), residual left as the
+                            // exact fp32 difference (the tensor core reads its top 19 bits); 0: cvt.rna on both, 1: masked residual.  Same measured
+                            // GEMM and gradient errors; 3 instead of ~9 ALU instructions per element: 1.2 % of a fine-tune step (same-box A/B)
 #endif
 __device__ __forceinline__ uint32_t to_tf32(float a) {
   uint32_t r;
@@ -96,7 +98,7 @@ __device__ __forceinline__ uint32_t idesc_tf32(int N) {
 
 // one 16-byte K chunk of one row -> the hi image and the lo image
 //   KCH = 8: 8 fp32 -> 8 bf16 heads + 8 bf16 residuals (a = hi + lo to 2^-18)
-//   KCH = 4: 4 fp32 -> 4 tf32 heads + 4 tf32 residuals (round-to-nearest both: a = hi + lo to 2^-23)
+//   KCH = 4: 4 fp32 -> 4 tf32 heads (round to nearest) + 4 residuals (exact in fp32, truncated to tf32 by the tensor core: a = hi + lo to 2^-21)
 template <int KCH>
 __device__ __forceinline__ void split_chunk(const float* v, uint32_t (&h)[4], uint32_t (&l)[4]) {
   if constexpr (KCH == 8) {
@@ -758,8 +760,14 @@ struct PackedRing {
   static constexpr uint32_t kABytes = 2 * kAHalf, kBBytes = 2 * kBH;
   static constexpr uint32_t kRawBytes = GM * 64;             // one fp32 stage of A as the tensor copy lands it: 128 rows x 64 B
   static constexpr int NSA = DUAL ? ZEST_GEMM_NSA_DUAL : 2;
-  static constexpr int NSB = DUAL ? (TMA_A ? 3 : ZEST_GEMM_NSB_DUAL) : 2;
-  static constexpr int NR = TMA_A ? 4 : 0;                   // fp32 landing slots of the A tensor copies
+#ifndef ZEST_GEMM_NSB_TMA
+#define ZEST_GEMM_NSB_TMA 3
+#endif
+#ifndef ZEST_GEMM_NR
+#define ZEST_GEMM_NR 4
+#endif
+  static constexpr int NSB = DUAL ? (TMA_A ? ZEST_GEMM_NSB_TMA : ZEST_GEMM_NSB_DUAL) : 2;
+  static constexpr int NR = TMA_A ? ZEST_GEMM_NR : 0;                   // fp32 landing slots of the A tensor copies
   static constexpr uint32_t kBRing = NSA * kABytes, kRawRing = kBRing + NSB * kBBytes;
   static constexpr uint32_t kBytes = kRawRing + NR * kRawBytes;
   static constexpr uint32_t kTail = 256;                     // barriers + TMEM base behind the rings
