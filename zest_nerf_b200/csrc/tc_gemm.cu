@@ -746,7 +746,10 @@ int g_tl_meta[kTlLaunches][8];
 // register staging a stage took ~2200 cycles while the loads of stage + 6 were being issued and ~1000 without - the LSU path
 // (8 half-lines per LDG.128, 2 CTAs x 96 KB in flight) was the bound, not HBM (39 %), the tensor pipe (26 %) or the ALU split
 // (a 3x cheaper split changed nothing).  Tensor copies take the loads off the LSU: 0.615 -> 0.440 ms.
-// The ring split 2 A + 4 B (vs 3 + 3) was worth 2 %; 112 KB rings lose the second CTA and are slower.
+// The ring split 2 A + 4 B (vs 3 + 3) was worth 2 % on the register path; rings above 113 KB lose the second CTA and are slower.
+// Tensor-copy path, same-box A/B of the whole fine-tune step (A slots / B slots / landing slots, all 112 KB): 2 / 3 / 4 = 74.4 ms
+// (shipped), 2 / 3 / 3 = 77.6, 2 / 4 / 2 = 80.4, 3 / 2 / 4 = 79.2, 2 / 2 / 6 = 79.6: both the weight copies and the landing ring
+// want depth; a third A slot buys nothing.
 #ifndef ZEST_GEMM_NSA_DUAL
 #define ZEST_GEMM_NSA_DUAL 2
 #endif
